@@ -1,0 +1,664 @@
+// mcd_api.cu -- the C ABI of libmcd.so (include/mcd.h): context, tables, runs, drains, unit hooks.
+// No C++ exception crosses the boundary; every entry point returns an mcd_status.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+#include <vector>
+
+#include "mcd_internal.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+constexpr double kPiEFour = 6.51408491409531e-14;     // parameters.py:7
+constexpr double kBohrM = 5.29177210544e-11;          // scipy.constants 'Bohr radius' (CODATA 2022), parameters.py:8
+constexpr uint64_t kStatsWords = MCD_HIST_TOTAL + sizeof(mcd_counters) / 8;
+
+struct HostTable {
+  float* cdf = nullptr;
+  float* Es = nullptr;
+  float* Ws = nullptr;
+  int* nvalid = nullptr;
+  uint32_t nE = 0, nW = 0;
+};
+
+}  // namespace
+
+struct mcd_ctx {
+  int device = 0;
+  int sm_count = 0;
+  mcd_params par;
+  mcd_material mat;
+  DevParams P;
+  HostTable tab[MCD_MAX_TABLES];
+  // outputs
+  mcd_el_row* els = nullptr;
+  uint64_t max_el = 0;
+  uint32_t* scats = nullptr;
+  uint64_t seg_cap = 0;
+  unsigned int* seg_count = nullptr;
+  unsigned long long* ticket = nullptr;
+  unsigned long long* stats = nullptr;
+  int n_blocks = 0;
+  TrajLaunchInfo li{};
+  // last run
+  uint64_t last_count = 0;
+  bool seg_cached = false;
+  std::vector<uint64_t> seg_prefix;           // n_blocks + 1
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+  std::string err;
+};
+
+namespace {
+
+int fail(mcd_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  if (ctx) ctx->err = buf;
+  return code;
+}
+
+#define CU(ctx, call)                                                                          \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess)                                                                    \
+      return fail(ctx, e__ == cudaErrorMemoryAllocation ? MCD_ERR_NOMEM : MCD_ERR_CUDA,        \
+                  "%s failed: %s", #call, cudaGetErrorString(e__));                            \
+  } while (0)
+
+double gryz_sigma_host(double E, double Es, double ns) {          // crossSections.py:213-242
+  if (E <= Es) return 0.0;
+  const double U = E / Es;
+  return ns * kPiEFour * pow((U - 1.) / (U + 1.), 1.5) *
+         (1. + (2. * (1. - (1. / (2. * U))) / 3. * log(2.7 + sqrt(U - 1.)))) / (E * Es);
+}
+
+void build_dev_params(mcd_ctx* c) {
+  const mcd_params& p = c->par;
+  const mcd_material& mt = c->mat;
+  DevParams& P = c->P;
+  memset(&P, 0, sizeof P);
+  DevMat& m = P.m;
+  const double scale = mt.atnd * 1e-14;                            // scattering.py:35
+  const double Z = (double)mt.Z;
+  m.sig_scale_inv = (float)(1.0 / scale);
+  const double aZ = 3.4 * pow(Z, 0.666667);                        // crossSections.py:27
+  m.aZ = (float)aZ;
+  m.cR = (float)(5.21e-21 * Z * Z * 1e6 * 4.0 * M_PI * scale / aZ);
+  m.cM = (float)(mt.n_val * kPiEFour * scale);
+  m.Wc = (float)p.Wc;
+  const double b = mt.plasmon_e / mt.fermi_e;
+  m.cQ = (float)(mt.plasmon_e * 1e-10 / (2.0 * kBohrM));
+  m.Kq = (float)((sqrt(1.0 + b) - 1.0) / b);
+  m.inv_Ef = (float)(1.0 / mt.fermi_e);
+  m.bq = (float)b;
+  m.Ef = (float)mt.fermi_e;
+  m.Epl = (float)mt.plasmon_e;
+  m.nshell = mt.n_shells;
+  // Gryzinski slots: expected descending sigma at E0 (stable) so the in-kernel order check passes
+  int order[MCD_MAX_SHELLS];
+  double sg[MCD_MAX_SHELLS];
+  for (int i = 0; i < mt.n_shells; ++i) {
+    order[i] = i;
+    sg[i] = gryz_sigma_host(p.E0, mt.shell_E[i], mt.shell_n[i]);
+  }
+  for (int i = 1; i < mt.n_shells; ++i) {                          // stable insertion sort, descending
+    const int o = order[i];
+    int j = i;
+    while (j > 0 && sg[order[j - 1]] < sg[o]) { order[j] = order[j - 1]; --j; }
+    order[j] = o;
+  }
+  for (int k = 0; k < MCD_MAX_SHELLS; ++k) {
+    const int i = k < mt.n_shells ? order[k] : 0;
+    const bool on = k < mt.n_shells;
+    m.gShell[k] = on ? i : 0;
+    m.gE[k] = on ? (float)mt.shell_E[i] : 3.0e38f;                 // unused slots: never ionisable
+    m.gInvE[k] = on ? (float)(1.0 / mt.shell_E[i]) : 0.f;
+    m.gC[k] = on ? (float)(mt.shell_n[i] * kPiEFour * scale / mt.shell_E[i]) : 0.f;
+    m.sN[k] = on ? (float)mt.shell_n[k] : 0.f;
+    m.sInvE[k] = on ? (float)(1.0 / mt.shell_E[k]) : 1.f;
+  }
+  const double J = (mt.Z >= 13) ? (9.76 * Z + 58.5 / pow(Z, 0.19)) : 11.5 * Z;   // stoppingPowers.py:134-137
+  m.spC = (float)(2.0 * kPiEFour * mt.atnd * 1e-14);
+  m.Zf = (float)Z;
+  m.J = (float)J;
+  m.kJ = (float)(mt.bethe_k * J);
+  m.n_val = (float)mt.n_val;
+  m.inv_Eval = (float)(1.0 / mt.E_val);
+
+  P.E0 = (float)p.E0;
+  P.Emin = (float)p.Emin;
+  P.thickness = (float)p.thickness;
+  const double t = p.s_tilt_deg * M_PI / 180.0;                    // multiScatter.py:97-100
+  P.d0x = (float)(-sin(t));
+  P.d0y = 0.f;
+  P.d0z = (float)cos(t);
+  P.maxScatt = (int)(p.maxScatt > 0x7fffffff ? 0x7fffffff : p.maxScatt);
+  P.mode = p.mode;
+  P.bethe = p.bethe;
+  P.gryz_per_shell = (p.gryz_table_mode == MCD_GRYZ_PER_SHELL);
+  P.seed_lo = (uint32_t)p.seed;
+  P.seed_hi = (uint32_t)(p.seed >> 32);
+  P.scat_mask = p.scat_mask;
+  P.flags = p.flags;
+  // histogram axes: energy [Emin,E0], depth [0, 2R], R = E0 / S_Bethe,classical(E0)
+  P.hist.e_lo = (float)p.Emin;
+  P.hist.e_scale = (float)(MCD_HIST_E_BINS / (p.E0 - p.Emin));
+  const double sp0 = 2.0 * kPiEFour * mt.atnd * (Z / p.E0) * log(1.166 * p.E0 / J) * 1e-14;
+  P.hist.depth_scale = (float)(MCD_HIST_DEPTH_BINS / (2.0 * p.E0 / sp0));
+}
+
+void layout_of(uint32_t mask, mcd_scat_layout* L) {
+  int w = 2;
+  for (int b = 0; b < 16; ++b) L->word_of[b] = -1;
+  L->word_of[0] = (mask & MCD_SC_TYPE) ? 1 : -1;
+  const uint32_t three = MCD_SC_POSITION | MCD_SC_DIRECTION;
+  for (int b = 1; b <= 8; ++b) {
+    if (!(mask & (1u << b))) continue;
+    L->word_of[b] = w;
+    w += ((1u << b) & three) ? 3 : 1;
+  }
+  L->row_words = (mask & 0x1ffu) ? (uint32_t)w : 0u;
+}
+
+void refresh_tables(mcd_ctx* c) {
+  for (int s = 0; s < MCD_MAX_TABLES; ++s) {
+    DevTable& d = c->P.tab[s];
+    const HostTable& h = c->tab[s];
+    d.cdf = h.cdf; d.Es = h.Es; d.Ws = h.Ws; d.nvalid = h.nvalid;
+    d.nE = (int)h.nE; d.nW = (int)h.nW;
+  }
+}
+
+void free_table(HostTable& h) {
+  cudaFree(h.cdf); cudaFree(h.Es); cudaFree(h.Ws); cudaFree(h.nvalid);
+  h = HostTable();
+}
+
+int alloc_table(mcd_ctx* c, int slot, const float* Es, uint32_t nE, const float* Ws, uint32_t nW) {
+  if (slot < 0 || slot >= MCD_MAX_TABLES) return fail(c, MCD_ERR_INVALID, "table slot %d out of range", slot);
+  if (nE < 2 || nW < 3 || !Es || !Ws) return fail(c, MCD_ERR_INVALID, "table axes too small (nE=%u nW=%u)", nE, nW);
+  HostTable& h = c->tab[slot];
+  free_table(h);
+  CU(c, cudaMalloc(&h.cdf, (size_t)nE * (nW - 1) * sizeof(float)));
+  CU(c, cudaMalloc(&h.Es, nE * sizeof(float)));
+  CU(c, cudaMalloc(&h.Ws, nW * sizeof(float)));
+  CU(c, cudaMalloc(&h.nvalid, nE * sizeof(int)));
+  CU(c, cudaMemcpy(h.Es, Es, nE * sizeof(float), cudaMemcpyHostToDevice));
+  CU(c, cudaMemcpy(h.Ws, Ws, nW * sizeof(float), cudaMemcpyHostToDevice));
+  h.nE = nE;
+  h.nW = nW;
+  refresh_tables(c);
+  DevTable& d = c->P.tab[slot];
+  d.E_lo = Es[0];
+  d.inv_dE = (float)((double)(nE - 1) / ((double)Es[nE - 1] - (double)Es[0]));
+  return MCD_OK;
+}
+
+// temporary device buffer for the unit hooks
+template <typename T>
+struct Tmp {
+  T* p = nullptr;
+  ~Tmp() { cudaFree(p); }
+  cudaError_t alloc(uint64_t n) { return cudaMalloc(&p, (n ? n : 1) * sizeof(T)); }
+  cudaError_t up(const T* h, uint64_t n) {
+    cudaError_t e = alloc(n);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(p, h, n * sizeof(T), cudaMemcpyHostToDevice);
+  }
+  cudaError_t down(T* h, uint64_t n) { return cudaMemcpy(h, p, n * sizeof(T), cudaMemcpyDeviceToHost); }
+};
+
+int need_ctx(mcd_ctx* c) {
+  if (!c) return fail(nullptr, MCD_ERR_INVALID, "null context");
+  cudaError_t e = cudaSetDevice(c->device);
+  if (e != cudaSuccess) return fail(c, MCD_ERR_CUDA, "cudaSetDevice(%d): %s", c->device, cudaGetErrorString(e));
+  return MCD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mcd_abi_version(void) { return MCD_ABI_VERSION; }
+
+const char* mcd_last_error(const mcd_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+int mcd_device_count(int* n) {
+  if (!n) return fail(nullptr, MCD_ERR_INVALID, "null pointer");
+  int k = 0;
+  cudaError_t e = cudaGetDeviceCount(&k);
+  if (e != cudaSuccess || k == 0) {
+    *n = 0;
+    return fail(nullptr, MCD_ERR_NO_DEVICE, "no usable CUDA device (%s); libmcd has no CPU fallback",
+                e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+  }
+  *n = k;
+  return MCD_OK;
+}
+
+int mcd_device_info(int device, char* name, int name_len, int* sm_count, int* cc_major, int* cc_minor,
+                    uint64_t* total_mem) {
+  cudaDeviceProp pr;
+  cudaError_t e = cudaGetDeviceProperties(&pr, device);
+  if (e != cudaSuccess) return fail(nullptr, MCD_ERR_NO_DEVICE, "cudaGetDeviceProperties(%d): %s", device,
+                                    cudaGetErrorString(e));
+  if (name && name_len > 0) snprintf(name, name_len, "%s", pr.name);
+  if (sm_count) *sm_count = pr.multiProcessorCount;
+  if (cc_major) *cc_major = pr.major;
+  if (cc_minor) *cc_minor = pr.minor;
+  if (total_mem) *total_mem = (uint64_t)pr.totalGlobalMem;
+  return MCD_OK;
+}
+
+int mcd_create(const mcd_params* p, const mcd_material* m, int device, mcd_ctx** out) {
+  if (!p || !m || !out) return fail(nullptr, MCD_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (m->n_shells < 1 || m->n_shells > MCD_MAX_SHELLS)
+    return fail(nullptr, MCD_ERR_INVALID, "n_shells=%d outside 1..%d", m->n_shells, MCD_MAX_SHELLS);
+  if (p->mode != MCD_MODE_DS && p->mode != MCD_MODE_CONT) return fail(nullptr, MCD_ERR_INVALID, "bad mode %d", p->mode);
+  if (p->bethe < 0 || p->bethe > 2) return fail(nullptr, MCD_ERR_INVALID, "bad Bethe model %d", p->bethe);
+  if (p->elastic != MCD_ELASTIC_RUTH_VANILLA)
+    return fail(nullptr, MCD_ERR_INVALID, "only elastic = Ruth_vanilla is implemented");
+  if (!(p->E0 > p->Emin) || !(p->Emin > 0)) return fail(nullptr, MCD_ERR_INVALID, "need E0 > Emin > 0");
+  if (p->mode == MCD_MODE_DS && !(p->Emin > m->plasmon_e))
+    return fail(nullptr, MCD_ERR_INVALID, "DS needs Emin > plasmon energy (quinn_sigma, crossSections.py:272-281)");
+  if (p->maxScatt < 0) return fail(nullptr, MCD_ERR_INVALID, "maxScatt < 0");
+  int n = 0;
+  int rc = mcd_device_count(&n);
+  if (rc != MCD_OK) return rc;
+  if (device < 0 || device >= n) return fail(nullptr, MCD_ERR_INVALID, "device %d of %d", device, n);
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return fail(nullptr, MCD_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  mcd_ctx* c = new (std::nothrow) mcd_ctx();
+  if (!c) return fail(nullptr, MCD_ERR_NOMEM, "out of host memory");
+  c->device = device;
+  c->par = *p;
+  c->mat = *m;
+  cudaDeviceProp pr;
+  e = cudaGetDeviceProperties(&pr, device);
+  if (e != cudaSuccess) { delete c; return fail(nullptr, MCD_ERR_CUDA, "props: %s", cudaGetErrorString(e)); }
+  c->sm_count = pr.multiProcessorCount;
+  build_dev_params(c);
+  mcd_scat_layout L;
+  layout_of(p->scat_mask, &L);
+  c->P.scat_row_words = (int)L.row_words;
+  e = mcd_traj_max_blocks(c->P, c->sm_count, &c->li);
+  if (e != cudaSuccess) {
+    std::string msg = cudaGetErrorString(e);
+    delete c;
+    return fail(nullptr, MCD_ERR_CUDA, "trajectory kernel unusable on device %d (%s): %s -- libmcd is built for "
+                "sm_100a only and has no fallback", device, pr.name, msg.c_str());
+  }
+  c->n_blocks = c->li.blocks;
+  if ((e = cudaMalloc(&c->ticket, sizeof(unsigned long long))) != cudaSuccess ||
+      (e = cudaMalloc(&c->stats, kStatsWords * 8)) != cudaSuccess ||
+      (e = cudaMalloc(&c->seg_count, c->n_blocks * sizeof(unsigned int))) != cudaSuccess ||
+      (e = cudaMemset(c->stats, 0, kStatsWords * 8)) != cudaSuccess ||
+      (e = cudaMemset(c->seg_count, 0, c->n_blocks * sizeof(unsigned int))) != cudaSuccess ||
+      (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess) {
+    std::string msg = cudaGetErrorString(e);
+    mcd_destroy(c);
+    return fail(nullptr, MCD_ERR_CUDA, "context allocation: %s", msg.c_str());
+  }
+  c->seg_prefix.assign(c->n_blocks + 1, 0);
+  *out = c;
+  return MCD_OK;
+}
+
+int mcd_destroy(mcd_ctx* c) {
+  if (!c) return MCD_OK;
+  cudaSetDevice(c->device);
+  for (auto& t : c->tab) free_table(t);
+  cudaFree(c->els); cudaFree(c->scats); cudaFree(c->seg_count); cudaFree(c->ticket); cudaFree(c->stats);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  delete c;
+  return MCD_OK;
+}
+
+// ---- tables ------------------------------------------------------------------------------------
+int mcd_table_build(mcd_ctx* c, int slot, const float* Es, uint32_t nE, const float* Ws, uint32_t nW,
+                    double shell_E, double shell_n, void* stream) {
+  int rc = need_ctx(c);
+  if (rc) return rc;
+  rc = alloc_table(c, slot, Es, nE, Ws, nW);
+  if (rc) return rc;
+  HostTable& h = c->tab[slot];
+  TableBuildArgs a;
+  a.kind = slot == MCD_TABLE_MOLLER ? 0 : 1;
+  a.Es = h.Es; a.Ws = h.Ws; a.cdf = h.cdf; a.nvalid = h.nvalid;
+  a.nE = (int)nE; a.nW = (int)nW;
+  a.Ef32 = (float)c->mat.fermi_e;
+  a.numEl = a.kind == 0 ? c->mat.n_val : shell_n;
+  a.Eb = shell_E;
+  if (a.kind == 1 && !(shell_E > 0 && shell_n > 0)) return fail(c, MCD_ERR_INVALID, "Gryzinski table needs shell_E, shell_n");
+  int blocks = c->sm_count * 4;
+  if (blocks > (int)nE) blocks = (int)nE;
+  Tmp<double> scratch;
+  CU(c, scratch.alloc((uint64_t)blocks * (nW - 1)));
+  a.scratch = scratch.p;
+  CU(c, mcd_launch_table_build(a, blocks, (cudaStream_t)stream));
+  CU(c, cudaStreamSynchronize((cudaStream_t)stream));
+  return MCD_OK;
+}
+
+int mcd_table_upload(mcd_ctx* c, int slot, const float* Es, uint32_t nE, const float* Ws, uint32_t nW,
+                     const float* cdf) {
+  int rc = need_ctx(c);
+  if (rc) return rc;
+  if (!cdf) return fail(c, MCD_ERR_INVALID, "null cdf");
+  rc = alloc_table(c, slot, Es, nE, Ws, nW);
+  if (rc) return rc;
+  HostTable& h = c->tab[slot];
+  CU(c, cudaMemcpy(h.cdf, cdf, (size_t)nE * (nW - 1) * sizeof(float), cudaMemcpyHostToDevice));
+  CU(c, mcd_launch_table_nvalid(h.cdf, (int)nE, (int)nW, h.nvalid, 0));
+  CU(c, cudaDeviceSynchronize());
+  return MCD_OK;
+}
+
+int mcd_table_shape(const mcd_ctx* c, int slot, uint32_t* nE, uint32_t* nW) {
+  if (!c || slot < 0 || slot >= MCD_MAX_TABLES) return fail(nullptr, MCD_ERR_INVALID, "bad ctx/slot");
+  if (nE) *nE = c->tab[slot].nE;
+  if (nW) *nW = c->tab[slot].nW;
+  return MCD_OK;
+}
+
+int mcd_table_download(mcd_ctx* c, int slot, float* out) {
+  int rc = need_ctx(c);
+  if (rc) return rc;
+  if (slot < 0 || slot >= MCD_MAX_TABLES || !c->tab[slot].cdf || !out)
+    return fail(c, MCD_ERR_STATE, "table slot %d not present", slot);
+  const HostTable& h = c->tab[slot];
+  CU(c, cudaMemcpy(out, h.cdf, (size_t)h.nE * (h.nW - 1) * sizeof(float), cudaMemcpyDeviceToHost));
+  return MCD_OK;
+}
+
+// ---- runs --------------------------------------------------------------------------------------
+int mcd_set_capacity(mcd_ctx* c, uint64_t max_electrons, uint64_t max_scat_rows) {
+  int rc = need_ctx(c);
+  if (rc) return rc;
+  if (max_electrons == 0) return fail(c, MCD_ERR_INVALID, "max_electrons = 0");
+  if (max_electrons >> 32) return fail(c, MCD_ERR_INVALID, "at most 2^32-1 electrons per run (scats word 0 is 32 bit)");
+  cudaFree(c->els); c->els = nullptr;
+  cudaFree(c->scats); c->scats = nullptr;
+  c->max_el = 0; c->seg_cap = 0;
+  CU(c, cudaMalloc(&c->els, max_electrons * sizeof(mcd_el_row)));
+  c->max_el = max_electrons;
+  if (max_scat_rows && c->P.scat_row_words) {
+    const uint64_t cap = (max_scat_rows + c->n_blocks - 1) / c->n_blocks;
+    if (cap >> 32) return fail(c, MCD_ERR_INVALID, "scats segment too large");
+    CU(c, cudaMalloc(&c->scats, cap * c->n_blocks * (uint64_t)c->P.scat_row_words * 4));
+    c->seg_cap = cap;
+  }
+  return MCD_OK;
+}
+
+int mcd_scat_layout_get(const mcd_ctx* c, mcd_scat_layout* out) {
+  if (!c || !out) return fail(nullptr, MCD_ERR_INVALID, "null argument");
+  layout_of(c->par.scat_mask, out);
+  return MCD_OK;
+}
+
+int mcd_reset_stats(mcd_ctx* c, void* stream) {
+  int rc = need_ctx(c);
+  if (rc) return rc;
+  CU(c, cudaMemsetAsync(c->stats, 0, kStatsWords * 8, (cudaStream_t)stream));
+  return MCD_OK;
+}
+
+int mcd_run(mcd_ctx* c, uint64_t first_id, uint64_t count, void* stream) {
+  int rc = need_ctx(c);
+  if (rc) return rc;
+  if (!c->els) return fail(c, MCD_ERR_STATE, "mcd_set_capacity has not been called");
+  if (count == 0 || count > c->max_el) return fail(c, MCD_ERR_INVALID, "count %llu outside 1..%llu",
+                                                   (unsigned long long)count, (unsigned long long)c->max_el);
+  if (c->par.mode == MCD_MODE_DS) {
+    if (!c->tab[MCD_TABLE_MOLLER].cdf || !c->tab[MCD_TABLE_GRYZ0].cdf)
+      return fail(c, MCD_ERR_STATE, "DS mode needs the Moller table (slot 0) and Gryzinski table (slot 1)");
+    if (c->P.gryz_per_shell)
+      for (int k = 0; k < c->mat.n_shells; ++k)
+        if (!c->tab[MCD_TABLE_GRYZ0 + k].cdf) return fail(c, MCD_ERR_STATE, "per-shell mode: Gryzinski table %d missing", k);
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  CU(c, cudaMemsetAsync(c->ticket, 0, sizeof(unsigned long long), s));
+  CU(c, cudaMemsetAsync(c->seg_count, 0, c->n_blocks * sizeof(unsigned int), s));
+  DevOut O;
+  O.els = c->els;
+  O.scats = c->scats;
+  O.seg_cap_rows = c->seg_cap;
+  O.seg_count = c->seg_count;
+  O.ticket = c->ticket;
+  O.stats = c->stats;
+  CU(c, cudaEventRecord(c->ev0, s));
+  CU(c, mcd_launch_traj(c->P, O, first_id, count, c->sm_count, s, &c->li));
+  CU(c, cudaEventRecord(c->ev1, s));
+  c->last_count = count;
+  c->seg_cached = false;
+  c->timed = true;
+  return MCD_OK;
+}
+
+int mcd_sync(mcd_ctx* c, void* stream) {
+  int rc = need_ctx(c);
+  if (rc) return rc;
+  CU(c, cudaStreamSynchronize((cudaStream_t)stream));
+  return MCD_OK;
+}
+
+static int cache_segments(mcd_ctx* c) {
+  if (c->seg_cached) return MCD_OK;
+  std::vector<unsigned int> cnt(c->n_blocks);
+  CU(c, cudaMemcpy(cnt.data(), c->seg_count, c->n_blocks * sizeof(unsigned int), cudaMemcpyDeviceToHost));
+  c->seg_prefix[0] = 0;
+  for (int b = 0; b < c->n_blocks; ++b) c->seg_prefix[b + 1] = c->seg_prefix[b] + (c->scats ? cnt[b] : 0u);
+  c->seg_cached = true;
+  return MCD_OK;
+}
+
+int mcd_row_counts(mcd_ctx* c, uint64_t* n_els, uint64_t* n_scats) {
+  int rc = need_ctx(c);
+  if (rc) return rc;
+  rc = cache_segments(c);
+  if (rc) return rc;
+  if (n_els) *n_els = c->last_count;
+  if (n_scats) *n_scats = c->seg_prefix[c->n_blocks];
+  return MCD_OK;
+}
+
+int mcd_drain_els(mcd_ctx* c, mcd_el_row* host, uint64_t offset, uint64_t n, void* stream) {
+  int rc = need_ctx(c);
+  if (rc) return rc;
+  if (!host || offset + n > c->last_count) return fail(c, MCD_ERR_INVALID, "els range outside the last run");
+  if (n == 0) return MCD_OK;
+  CU(c, cudaMemcpyAsync(host, c->els + offset, n * sizeof(mcd_el_row), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return MCD_OK;
+}
+
+int mcd_drain_scats(mcd_ctx* c, uint32_t* host, uint64_t offset, uint64_t n, void* stream) {
+  int rc = need_ctx(c);
+  if (rc) return rc;
+  rc = cache_segments(c);
+  if (rc) return rc;
+  const uint64_t total = c->seg_prefix[c->n_blocks];
+  if (!host || offset + n > total) return fail(c, MCD_ERR_INVALID, "scats range outside the stored rows");
+  const uint64_t rw = (uint64_t)c->P.scat_row_words;
+  uint64_t done = 0;
+  for (int b = 0; b < c->n_blocks && done < n; ++b) {
+    const uint64_t lo = c->seg_prefix[b], hi = c->seg_prefix[b + 1];
+    const uint64_t from = offset + done;
+    if (from >= hi || lo == hi) continue;
+    const uint64_t k = (hi - from < n - done) ? hi - from : n - done;
+    const uint32_t* src = c->scats + ((uint64_t)b * c->seg_cap + (from - lo)) * rw;
+    CU(c, cudaMemcpyAsync(host + done * rw, src, k * rw * 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    done += k;
+  }
+  return MCD_OK;
+}
+
+int mcd_counters_get(mcd_ctx* c, mcd_counters* out) {
+  int rc = need_ctx(c);
+  if (rc) return rc;
+  if (!out) return fail(c, MCD_ERR_INVALID, "null pointer");
+  CU(c, cudaMemcpy(out, c->stats + MCD_HIST_TOTAL, sizeof(mcd_counters), cudaMemcpyDeviceToHost));
+  return MCD_OK;
+}
+
+int mcd_hist_get(mcd_ctx* c, int64_t* host) {
+  int rc = need_ctx(c);
+  if (rc) return rc;
+  if (!host) return fail(c, MCD_ERR_INVALID, "null pointer");
+  CU(c, cudaMemcpy(host, c->stats, MCD_HIST_TOTAL * 8, cudaMemcpyDeviceToHost));
+  return MCD_OK;
+}
+
+int mcd_stats_device_ptr(mcd_ctx* c, void** dev_ptr, uint64_t* n_int64) {
+  if (!c || !dev_ptr || !n_int64) return fail(nullptr, MCD_ERR_INVALID, "null argument");
+  *dev_ptr = c->stats;
+  *n_int64 = kStatsWords;
+  return MCD_OK;
+}
+
+int mcd_hist_ranges(const mcd_ctx* c, double* e_lo, double* e_hi, double* depth_max) {
+  if (!c) return fail(nullptr, MCD_ERR_INVALID, "null context");
+  if (e_lo) *e_lo = c->par.Emin;
+  if (e_hi) *e_hi = c->par.E0;
+  if (depth_max) *depth_max = (double)MCD_HIST_DEPTH_BINS / (double)c->P.hist.depth_scale;
+  return MCD_OK;
+}
+
+int mcd_last_kernel_ms(mcd_ctx* c, float* ms) {
+  int rc = need_ctx(c);
+  if (rc) return rc;
+  if (!ms || !c->timed) return fail(c, MCD_ERR_STATE, "no run has been timed");
+  CU(c, cudaEventSynchronize(c->ev1));
+  CU(c, cudaEventElapsedTime(ms, c->ev0, c->ev1));
+  return MCD_OK;
+}
+
+int mcd_launch_info(mcd_ctx* c, int* blocks, int* threads, int* regs, int* blocks_per_sm) {
+  if (!c) return fail(nullptr, MCD_ERR_INVALID, "null context");
+  if (blocks) *blocks = c->li.blocks;
+  if (threads) *threads = c->li.threads;
+  if (regs) *regs = c->li.regs;
+  if (blocks_per_sm) *blocks_per_sm = c->li.blocks_per_sm;
+  return MCD_OK;
+}
+
+// ---- unit hooks --------------------------------------------------------------------------------
+int mcd_test_sigmas(mcd_ctx* c, const float* E, uint64_t n, float* sigma_out, float* mfp_out) {
+  int rc = need_ctx(c);
+  if (rc) return rc;
+  const int nch = c->mat.n_shells + 3;
+  Tmp<float> dE, dS, dM;
+  CU(c, dE.up(E, n)); CU(c, dS.alloc(n * nch)); CU(c, dM.alloc(n));
+  CU(c, mcd_launch_test_sigmas(c->P, dE.p, n, dS.p, dM.p, 0));
+  CU(c, dS.down(sigma_out, n * nch)); CU(c, dM.down(mfp_out, n));
+  return MCD_OK;
+}
+
+int mcd_test_select(mcd_ctx* c, const float* sigma, int nch, const float* u, uint64_t n, int32_t* pick_out,
+                    int32_t* path_out) {
+  int rc = need_ctx(c);
+  if (rc) return rc;
+  if (nch < 1 || nch > MCD_MAX_CHANNELS) return fail(c, MCD_ERR_INVALID, "nch=%d outside 1..%d", nch, MCD_MAX_CHANNELS);
+  Tmp<float> dS, dU;
+  Tmp<int> dP, dQ;
+  CU(c, dS.up(sigma, n * nch)); CU(c, dU.up(u, n)); CU(c, dP.alloc(n)); CU(c, dQ.alloc(n));
+  CU(c, mcd_launch_test_select(dS.p, nch, dU.p, n, dP.p, dQ.p, 0));
+  CU(c, dP.down(pick_out, n));
+  if (path_out) CU(c, dQ.down(path_out, n));
+  return MCD_OK;
+}
+
+int mcd_test_ruth(mcd_ctx* c, const float* E, const float* u, uint64_t n, float* c2_out, float* om_out) {
+  int rc = need_ctx(c);
+  if (rc) return rc;
+  Tmp<float> dE, dU, dC, dO;
+  CU(c, dE.up(E, n)); CU(c, dU.up(u, n)); CU(c, dC.alloc(n)); CU(c, dO.alloc(n));
+  CU(c, mcd_launch_test_ruth(c->P, dE.p, dU.p, n, dC.p, dO.p, 0));
+  CU(c, dC.down(c2_out, n)); CU(c, dO.down(om_out, n));
+  return MCD_OK;
+}
+
+int mcd_test_bincoll(mcd_ctx* c, const float* E, const float* W, uint64_t n, float* c2_out, float* om_out) {
+  int rc = need_ctx(c);
+  if (rc) return rc;
+  Tmp<float> dE, dW, dC, dO;
+  CU(c, dE.up(E, n)); CU(c, dW.up(W, n)); CU(c, dC.alloc(n)); CU(c, dO.alloc(n));
+  CU(c, mcd_launch_test_bincoll(c->P, dE.p, dW.p, n, dC.p, dO.p, 0));
+  CU(c, dC.down(c2_out, n)); CU(c, dO.down(om_out, n));
+  return MCD_OK;
+}
+
+int mcd_test_rotate(mcd_ctx* c, const float* d_in, const float* y_in, const float* c2, const float* om,
+                    const float* u_phi, uint64_t n, float* d_out, float* y_out) {
+  int rc = need_ctx(c);
+  if (rc) return rc;
+  Tmp<float> dD, dY, dC, dO, dU, oD, oY;
+  CU(c, dD.up(d_in, 3 * n)); CU(c, dY.up(y_in, 3 * n)); CU(c, dC.up(c2, n)); CU(c, dO.up(om, n));
+  CU(c, dU.up(u_phi, n)); CU(c, oD.alloc(3 * n)); CU(c, oY.alloc(3 * n));
+  CU(c, mcd_launch_test_rotate(dD.p, dY.p, dC.p, dO.p, dU.p, n, oD.p, oY.p, 0));
+  CU(c, oD.down(d_out, 3 * n)); CU(c, oY.down(y_out, 3 * n));
+  return MCD_OK;
+}
+
+int mcd_test_stopping(mcd_ctx* c, int bethe, const float* E, uint64_t n, float* sp_out) {
+  int rc = need_ctx(c);
+  if (rc) return rc;
+  if (bethe < 0 || bethe > 2) return fail(c, MCD_ERR_INVALID, "bad Bethe model");
+  Tmp<float> dE, dS;
+  CU(c, dE.up(E, n)); CU(c, dS.alloc(n));
+  CU(c, mcd_launch_test_stopping(c->P, bethe, dE.p, n, dS.p, 0));
+  CU(c, dS.down(sp_out, n));
+  return MCD_OK;
+}
+
+int mcd_test_lookup(mcd_ctx* c, int slot, const float* E, const float* u, uint64_t n, float* W_out,
+                    int32_t* iE_out, int32_t* jW_out) {
+  int rc = need_ctx(c);
+  if (rc) return rc;
+  if (slot < 0 || slot >= MCD_MAX_TABLES || !c->tab[slot].cdf) return fail(c, MCD_ERR_STATE, "table slot %d not present", slot);
+  Tmp<float> dE, dU, dW;
+  Tmp<int> dI, dJ;
+  CU(c, dE.up(E, n)); CU(c, dU.up(u, n)); CU(c, dW.alloc(n)); CU(c, dI.alloc(n)); CU(c, dJ.alloc(n));
+  CU(c, mcd_launch_test_lookup(c->P, slot, dE.p, dU.p, n, dW.p, dI.p, dJ.p, 0));
+  CU(c, dW.down(W_out, n)); CU(c, dI.down(iE_out, n)); CU(c, dJ.down(jW_out, n));
+  return MCD_OK;
+}
+
+int mcd_test_step(mcd_ctx* c, const float* state_in, const float* u, uint64_t n, float* state_out, float* row_out) {
+  int rc = need_ctx(c);
+  if (rc) return rc;
+  if (c->par.mode == MCD_MODE_DS && (!c->tab[MCD_TABLE_MOLLER].cdf || !c->tab[MCD_TABLE_GRYZ0].cdf))
+    return fail(c, MCD_ERR_STATE, "DS step needs tables in slots 0 and 1");
+  Tmp<float> dS, dU, oS, oR;
+  CU(c, dS.up(state_in, 10 * n)); CU(c, dU.up(u, 4 * n)); CU(c, oS.alloc(10 * n)); CU(c, oR.alloc(8 * n));
+  CU(c, mcd_launch_test_step(c->P, dS.p, dU.p, n, oS.p, oR.p, 0));
+  CU(c, oS.down(state_out, 10 * n)); CU(c, oR.down(row_out, 8 * n));
+  return MCD_OK;
+}
+
+int mcd_test_philox(uint64_t seed, uint64_t el_id, uint32_t ev_idx, uint32_t raw_out[4], float u_out[4]) {
+  int n = 0;
+  int rc = mcd_device_count(&n);
+  if (rc) return rc;
+  Tmp<uint32_t> dR;
+  Tmp<float> dU;
+  CU(nullptr, dR.alloc(4)); CU(nullptr, dU.alloc(4));
+  CU(nullptr, mcd_launch_test_philox(seed, el_id, ev_idx, dR.p, dU.p, 0));
+  CU(nullptr, dR.down(raw_out, 4)); CU(nullptr, dU.down(u_out, 4));
+  return MCD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,52 @@
+// mcd_internal.h -- host-side declarations shared by the translation units of libmcd.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/mcd.h"
+#include "mcd_device.cuh"
+
+struct TableBuildArgs {
+  int kind;                 // 0 Moller, 1 Gryzinski
+  const float* Es;          // device, nE
+  const float* Ws;          // device, nW
+  float* cdf;               // device, nE x (nW-1)
+  int* nvalid;              // device, nE
+  double* scratch;          // device, gridDim.x x (nW-1)
+  int nE, nW;
+  float Ef32;               // float32(Ef): (E - Ef)*0.5 is float32 arithmetic in the reference
+  double numEl;             // n_val (Moller) or ns (Gryzinski)
+  double Eb;                // shell binding energy (Gryzinski), python float in the reference
+};
+
+struct TrajLaunchInfo {
+  int blocks, threads, regs, blocks_per_sm;
+};
+
+// mcd_traj.cu
+cudaError_t mcd_launch_traj(const DevParams& P, const DevOut& O, unsigned long long first_id,
+                            unsigned long long count, int sm_count, cudaStream_t stream, TrajLaunchInfo* info);
+cudaError_t mcd_traj_max_blocks(const DevParams& P, int sm_count, TrajLaunchInfo* info);
+
+// mcd_tables.cu
+cudaError_t mcd_launch_table_build(const TableBuildArgs& a, int blocks, cudaStream_t stream);
+cudaError_t mcd_launch_table_nvalid(const float* cdf, int nE, int nW, int* nvalid, cudaStream_t stream);
+
+// mcd_unit.cu
+cudaError_t mcd_launch_test_sigmas(const DevParams& P, const float* E, uint64_t n, float* sig, float* mfp,
+                                   cudaStream_t s);
+cudaError_t mcd_launch_test_select(const float* sigma, int nch, const float* u, uint64_t n, int* pick, int* path,
+                                   cudaStream_t s);
+cudaError_t mcd_launch_test_ruth(const DevParams& P, const float* E, const float* u, uint64_t n, float* c2,
+                                 float* om, cudaStream_t s);
+cudaError_t mcd_launch_test_bincoll(const DevParams& P, const float* E, const float* W, uint64_t n, float* c2,
+                                    float* om, cudaStream_t s);
+cudaError_t mcd_launch_test_rotate(const float* d, const float* y, const float* c2, const float* om,
+                                   const float* u, uint64_t n, float* d_out, float* y_out, cudaStream_t s);
+cudaError_t mcd_launch_test_stopping(const DevParams& P, int bethe, const float* E, uint64_t n, float* sp,
+                                     cudaStream_t s);
+cudaError_t mcd_launch_test_lookup(const DevParams& P, int slot, const float* E, const float* u, uint64_t n,
+                                   float* W, int* iE, int* jW, cudaStream_t s);
+cudaError_t mcd_launch_test_step(const DevParams& P, const float* st, const float* u, uint64_t n, float* st_out,
+                                 float* row_out, cudaStream_t s);
+cudaError_t mcd_launch_test_philox(uint64_t seed, uint64_t el, uint32_t ev, uint32_t* raw, float* u,
+                                   cudaStream_t s);

@@ -1,0 +1,248 @@
+// mcd_traj.cu -- K1/K2: persistent one-thread-per-electron trajectory kernels (sm_100a).
+//
+// Replaces the job loop of multiTraj_DS / multiTraj_cont (MC/tools/multiScatter.py:66-116, 171-229) and
+// the while-loops of trajectory_DS / trajectory_cont_cl (MC/tools/singleScatter.py:10-41, 205-239).
+//
+//  * grid = resident blocks only (SMs x occupancy); a lane whose electron ended takes the next id from
+//    a global ticket (one warp-aggregated atomic per refill) so warps stay full until ids run out;
+//  * RNG = Philox4x32-10, key = seed, counter = (electron id, event index): results do not depend on
+//    which lane / block / GPU runs an electron;
+//  * outputs: one 32-byte els row per electron at index id - first_id; scats rows appended per block
+//    (shared-memory cursor, one warp-aggregated reservation per event) into that block's segment;
+//    backscatter histograms and counters accumulate in shared memory and are flushed once per block.
+#include "mcd_internal.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kCntOutcome = 0;       // 5
+constexpr int kCntEvents = 5;
+constexpr int kCntDone = 6;
+constexpr int kCntDouble = 7;
+constexpr int kCntNan = 8;
+constexpr int kCntExact = 9;
+constexpr int kCntChan = 10;         // MCD_MAX_CHANNELS
+constexpr int kCntTotal = kCntChan + MCD_MAX_CHANNELS;
+
+__device__ __forceinline__ unsigned lanemask_lt() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+__device__ __forceinline__ void store_scat_row(uint32_t* __restrict__ dst, uint32_t mask, uint32_t rel_id,
+                                               uint32_t ev, const EventRow& r, const ElState& e) {
+  int w = 0;
+  dst[w++] = rel_id;
+  dst[w++] = (ev & 0xffffffu) | ((uint32_t)r.channel << 24);
+  if (mask & MCD_SC_POSITION) {
+    dst[w++] = __float_as_uint(r.px); dst[w++] = __float_as_uint(r.py); dst[w++] = __float_as_uint(r.pz);
+  }
+  if (mask & MCD_SC_PATHL) dst[w++] = __float_as_uint(r.pathl);
+  if (mask & MCD_SC_E) dst[w++] = __float_as_uint(r.E);
+  if (mask & MCD_SC_E_LOSS) dst[w++] = __float_as_uint(r.E_loss);
+  if (mask & MCD_SC_POL_ANGLE) dst[w++] = __float_as_uint(r.c2);
+  if (mask & MCD_SC_AZ_ANGLE) dst[w++] = __float_as_uint(r.halfPhi);
+  if (mask & MCD_SC_ENERGY) dst[w++] = __float_as_uint(r.energy);
+  if (mask & MCD_SC_DIRECTION) {
+    dst[w++] = __float_as_uint(e.dx); dst[w++] = __float_as_uint(e.dy); dst[w++] = __float_as_uint(e.dz);
+  }
+}
+
+template <int S, int MODE>
+__global__ void __launch_bounds__(kThreads)
+traj_kernel(const __grid_constant__ DevParams P, const DevOut O, const unsigned long long first_id,
+            const unsigned long long count) {
+  __shared__ unsigned int s_hist[MCD_HIST_TOTAL];
+  __shared__ unsigned long long s_cnt[kCntTotal];
+  __shared__ unsigned int s_cursor;
+
+  for (int i = threadIdx.x; i < MCD_HIST_TOTAL; i += kThreads) s_hist[i] = 0u;
+  for (int i = threadIdx.x; i < kCntTotal; i += kThreads) s_cnt[i] = 0ull;
+  if (threadIdx.x == 0) s_cursor = 0u;
+  __syncthreads();
+
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned lt = lanemask_lt();
+  const bool want_scats = (P.scat_row_words > 0) && (O.scats != nullptr);
+  const bool want_hist = (P.flags & MCD_FLAG_HISTOGRAMS) != 0u;
+  const bool want_chan = (P.flags & MCD_FLAG_CHANNEL_COUNTS) != 0u;
+  uint32_t* const seg = want_scats
+      ? O.scats + (size_t)blockIdx.x * (size_t)O.seg_cap_rows * (size_t)P.scat_row_words : nullptr;
+
+  bool alive = false, exhausted = false;
+  ElState e;
+  unsigned long long rel_id = 0ull;
+  uint32_t ev = 0u;
+  unsigned int my_events = 0u;
+
+  while (true) {
+    // ---- refill dead lanes (multiScatter.py:105-107: a fresh electron at pos0 / dir0) ----------
+    const unsigned need = __ballot_sync(MCD_FULL_MASK, !alive && !exhausted);
+    if (need) {
+      const int leader = __ffs(need) - 1;
+      unsigned long long base = 0ull;
+      if ((int)lane == leader) base = atomicAdd(O.ticket, (unsigned long long)__popc(need));
+      base = __shfl_sync(MCD_FULL_MASK, base, leader);
+      if (!alive && !exhausted) {
+        rel_id = base + (unsigned long long)__popc(need & lt);
+        if (rel_id < count) {
+          alive = true;
+          ev = 0u;
+          e.E = P.E0;
+          e.x = 0.f; e.y = 0.f; e.z = 0.f;
+          e.dx = P.d0x; e.dy = P.d0y; e.dz = P.d0z;
+          e.yx = 0.f; e.yy = 1.f; e.yz = 0.f;                    // electron.py:38
+        } else {
+          exhausted = true;
+        }
+      }
+    }
+    if (!__any_sync(MCD_FULL_MASK, alive)) break;
+
+    // ---- one loop iteration of trajectory_DS / trajectory_cont_cl ---------------------------
+    bool has_row = false;
+    int outcome = -1;
+    EventRow row;
+    OutcomeSnap sn;
+    row.flags = 0;
+    if (alive) {
+      if ((long long)ev >= (long long)P.maxScatt) {              // singleScatter.py:19-23
+        outcome = MCD_OUT_LONG;
+        snap(sn, e);
+      } else {
+        const float4 u = event_uniforms(P, first_id + rel_id, ev);
+        if (MODE == MCD_MODE_DS) ds_event<S>(P, e, u, row, sn);
+        else cont_event(P, e, u, row, sn);
+        has_row = true;
+        outcome = row.outcome;
+        ++my_events;
+      }
+    }
+
+    // ---- scats append: one reservation per warp per event ------------------------------------
+    if (want_scats) {
+      const unsigned m = __ballot_sync(MCD_FULL_MASK, has_row);
+      if (m) {
+        const int leader = __ffs(m) - 1;
+        unsigned int base = 0u;
+        if ((int)lane == leader) base = atomicAdd(&s_cursor, (unsigned int)__popc(m));
+        base = __shfl_sync(MCD_FULL_MASK, base, leader);
+        if (has_row) {
+          const unsigned long long r = (unsigned long long)base + (unsigned long long)__popc(m & lt);
+          if (r < O.seg_cap_rows)
+            store_scat_row(seg + r * (unsigned long long)P.scat_row_words, P.scat_mask, (uint32_t)rel_id, ev, row, e);
+        }
+      }
+    }
+    if (has_row) {
+      if (want_chan) atomicAdd(&s_cnt[kCntChan + row.channel], 1ull);
+      if (row.flags & MCD_EVF_NANCLAMP) atomicAdd(&s_cnt[kCntNan], 1ull);
+      if (row.flags & MCD_EVF_EXACT) atomicAdd(&s_cnt[kCntExact], 1ull);
+      ++ev;
+    }
+
+    // ---- retire: saveOutcomes row (electron.py:105-113), histograms, counters -------------------
+    if (outcome >= 0) {
+      const bool dbl = (row.flags & MCD_EVF_DOUBLE) != 0;
+      float4* dst = reinterpret_cast<float4*>(O.els + rel_id);
+      dst[0] = make_float4(__uint_as_float((uint32_t)outcome | (dbl ? 0x100u : 0u)), sn.E, sn.dx, sn.dy);
+      dst[1] = make_float4(sn.dz, sn.x, sn.y, sn.z);
+      atomicAdd(&s_cnt[kCntOutcome + outcome], 1ull);
+      atomicAdd(&s_cnt[kCntDone], 1ull);
+      atomicAdd(&s_cnt[kCntEvents], (unsigned long long)my_events);
+      if (dbl) atomicAdd(&s_cnt[kCntDouble], 1ull);
+      my_events = 0u;
+      if (want_hist && outcome == MCD_OUT_BKS) {
+        int b = (int)((sn.E - P.hist.e_lo) * P.hist.e_scale);
+        b = max(0, min(b, MCD_HIST_E_BINS - 1));
+        atomicAdd(&s_hist[b], 1u);
+        const float pol = acosf(fminf(1.0f, fmaxf(-1.0f, -sn.dz))) * 57.29577951308232f;      // from -z normal
+        b = max(0, min((int)(pol * 2.0f), MCD_HIST_POLAR_BINS - 1));
+        atomicAdd(&s_hist[MCD_HIST_E_BINS + b], 1u);
+        const float az = atan2f(sn.dy, sn.dx) * 57.29577951308232f + 180.0f;
+        b = max(0, min((int)az, MCD_HIST_AZ_BINS - 1));
+        atomicAdd(&s_hist[MCD_HIST_E_BINS + MCD_HIST_POLAR_BINS + b], 1u);
+        b = max(0, min((int)(sn.z * P.hist.depth_scale), MCD_HIST_DEPTH_BINS - 1));
+        atomicAdd(&s_hist[MCD_HIST_E_BINS + MCD_HIST_POLAR_BINS + MCD_HIST_AZ_BINS + b], 1u);
+      }
+      alive = false;
+    }
+  }
+
+  // ---- flush block statistics ------------------------------------------------------------------
+  __syncthreads();
+  for (int i = threadIdx.x; i < MCD_HIST_TOTAL; i += kThreads) {
+    const unsigned int v = s_hist[i];
+    if (v) atomicAdd(O.stats + i, (unsigned long long)v);
+  }
+  unsigned long long* cnt = O.stats + MCD_HIST_TOTAL;
+  // mcd_counters layout: electrons_done, events, outcome[5], double_records, stored, dropped, nan, exact, channel[]
+  if (threadIdx.x == 0) {
+    atomicAdd(cnt + 0, s_cnt[kCntDone]);
+    atomicAdd(cnt + 1, s_cnt[kCntEvents]);
+    for (int i = 0; i < 5; ++i) if (s_cnt[kCntOutcome + i]) atomicAdd(cnt + 2 + i, s_cnt[kCntOutcome + i]);
+    if (s_cnt[kCntDouble]) atomicAdd(cnt + 7, s_cnt[kCntDouble]);
+    if (want_scats) {
+      const unsigned long long appended = s_cursor;
+      const unsigned long long stored = appended < O.seg_cap_rows ? appended : O.seg_cap_rows;
+      O.seg_count[blockIdx.x] = (unsigned int)stored;
+      atomicAdd(cnt + 8, stored);
+      if (appended > stored) atomicAdd(cnt + 9, appended - stored);
+    }
+    if (s_cnt[kCntNan]) atomicAdd(cnt + 10, s_cnt[kCntNan]);
+    if (s_cnt[kCntExact]) atomicAdd(cnt + 11, s_cnt[kCntExact]);
+    if (want_chan)
+      for (int i = 0; i < MCD_MAX_CHANNELS; ++i)
+        if (s_cnt[kCntChan + i]) atomicAdd(cnt + 12 + i, s_cnt[kCntChan + i]);
+  }
+}
+
+typedef void (*TrajKernel)(const DevParams, const DevOut, const unsigned long long, const unsigned long long);
+
+TrajKernel pick_kernel(const DevParams& P) {
+  if (P.mode == MCD_MODE_CONT) return traj_kernel<1, MCD_MODE_CONT>;
+  switch (P.m.nshell) {
+    case 1: return traj_kernel<1, MCD_MODE_DS>;
+    case 2: return traj_kernel<2, MCD_MODE_DS>;
+    case 3: return traj_kernel<3, MCD_MODE_DS>;
+    case 4: return traj_kernel<4, MCD_MODE_DS>;
+    case 5: return traj_kernel<5, MCD_MODE_DS>;
+    case 6: return traj_kernel<6, MCD_MODE_DS>;
+    case 7: return traj_kernel<7, MCD_MODE_DS>;
+    case 8: return traj_kernel<8, MCD_MODE_DS>;
+    default: return nullptr;
+  }
+}
+
+}  // namespace
+
+cudaError_t mcd_traj_max_blocks(const DevParams& P, int sm_count, TrajLaunchInfo* info) {
+  TrajKernel k = pick_kernel(P);
+  if (!k) return cudaErrorInvalidValue;
+  int per_sm = 0;
+  cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kThreads, 0);
+  if (err != cudaSuccess) return err;
+  cudaFuncAttributes fa;
+  err = cudaFuncGetAttributes(&fa, k);
+  if (err != cudaSuccess) return err;
+  if (per_sm < 1) per_sm = 1;
+  info->blocks = per_sm * sm_count;
+  info->threads = kThreads;
+  info->regs = fa.numRegs;
+  info->blocks_per_sm = per_sm;
+  return cudaSuccess;
+}
+
+cudaError_t mcd_launch_traj(const DevParams& P, const DevOut& O, unsigned long long first_id,
+                            unsigned long long count, int sm_count, cudaStream_t stream, TrajLaunchInfo* info) {
+  TrajKernel k = pick_kernel(P);
+  if (!k) return cudaErrorInvalidValue;
+  TrajLaunchInfo li;
+  cudaError_t err = mcd_traj_max_blocks(P, sm_count, &li);
+  if (err != cudaSuccess) return err;
+  // the grid is always the full resident set: scats segments are sized per block of this grid
+  if (info) *info = li;
+  k<<<li.blocks, kThreads, 0, stream>>>(P, O, first_id, count);
+  return cudaGetLastError();
+}

@@ -1,0 +1,356 @@
+"""Engine: one libmcd context on one GPU -- the batched replacement for the reference's worker pool
+(MC/doScatter.py:22-95 MapScatterer + MC/tools/multiScatter.py:66-116,171-229 workers).
+
+PyTorch is used for plumbing only (pinned host buffers, the current CUDA stream, torch.distributed);
+all physics runs inside libmcd.so."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, fptr, iptr, f32
+from .material import material as Material, as_c_material
+
+DEFAULT_SEED = 12345
+
+
+def _mask(names, bits):
+    m = 0
+    for n in names:
+        if n not in bits:
+            raise ValueError('unknown output column %r (known: %s)' % (n, ', '.join(bits)))
+        m |= bits[n]
+    return m
+
+
+class RunResult:
+    """Columnar output of one run.
+
+    els   : structured array (code, final_E, dx, dy, dz, last_x, last_y, last_z), row i = electron first_id+i
+    scats : dict of column arrays in append order, with 'el' (absolute electron id) and 'ev' (event index)
+    """
+
+    def __init__(self, first_id, count, els, scats, counters, kernel_ms):
+        self.first_id, self.count = first_id, count
+        self.els, self.scats, self.counters, self.kernel_ms = els, scats, counters, kernel_ms
+
+    @property
+    def outcome(self):
+        return (self.els['code'] & 0xff).astype(np.int8)
+
+    @property
+    def double_record(self):
+        return (self.els['code'] & 0x100) != 0
+
+    def sorted_scats(self):
+        """scats columns regrouped per electron in event order (the reference's row order)."""
+        if not self.scats:
+            return self.scats
+        order = np.lexsort((self.scats['ev'], self.scats['el']))
+        return {k: v[order] for k, v in self.scats.items()}
+
+
+class Engine:
+    def __init__(self, inputPar, material=None, device=None, seed=None, gryz_table='outermost',
+                 histograms=True, channel_counts=False):
+        self.lib = _lib.load()
+        self.inputPar = dict(inputPar)
+        self.material = material if material is not None else Material(inputPar['material'])
+        self.gryz_mode = gryz_table
+        if device is None:
+            device = 0
+            try:
+                import torch
+                if torch.cuda.is_available():
+                    device = torch.cuda.current_device()
+            except Exception:
+                pass
+        self.device = int(device)
+        ip = self.inputPar
+        if ip.get('diffMFP', False):
+            raise NotImplementedError('diffMFP: yes crashes in the reference (scattering.py:512) and is not implemented')
+        p = _lib.Params()
+        p.E0, p.Emin = float(ip['E0']), float(ip['Emin'])
+        p.s_tilt_deg = float(ip['s_tilt'])
+        p.thickness = float(ip.get('thickness', 3e6))
+        p.Wc = float(ip.get('Wc', 10.))
+        p.tol_E, p.tol_W = float(ip.get('tol_E', 0)), float(ip.get('tol_W', 0))
+        p.maxScatt = int(ip['maxScatt'])
+        mode = ip['mode']
+        p.mode = _lib.MODE_DS if 'DS' in mode else _lib.MODE_CONT
+        if p.mode == _lib.MODE_CONT and 'cont' not in mode:
+            raise ValueError("mode must be 'DS' or 'cont' (got %r)" % mode)
+        bm = ip.get('Bethe_model', 'classical')
+        if bm not in _lib.BETHE:
+            raise ValueError('! I did not understand your choice of Bethe model: %r' % bm)
+        p.bethe = _lib.BETHE[bm]
+        if ip.get('elastic', 'Ruth_vanilla') != 'Ruth_vanilla':
+            raise NotImplementedError("only elastic = 'Ruth_vanilla' is implemented (others crash or need "
+                                      "unshipped data in the reference, SURVEY Q10)")
+        p.elastic = 0
+        p.gryz_table_mode = 1 if gryz_table == 'per_shell' else 0
+        self.el_cols = list(ip.get('electron_output', ['outcome', 'final_E', 'final_dir', 'last_pos']))
+        self.scat_cols = list(ip.get('scatter_output', []))
+        p.el_mask = _mask(self.el_cols, _lib.EL_BITS)
+        scat_cols = self.scat_cols
+        if p.mode == _lib.MODE_CONT:      # continuous mode never records position / E (scattering.py:802-840)
+            scat_cols = [c for c in scat_cols if c not in ('position', 'E')]
+        p.scat_mask = _mask(scat_cols, _lib.SC_BITS)
+        p.flags = (_lib.FLAG_HISTOGRAMS if histograms else 0) | (_lib.FLAG_CHANNEL_COUNTS if channel_counts else 0)
+        p.seed = int(seed if seed is not None else ip.get('seed', DEFAULT_SEED)) & 0xffffffffffffffff
+        self.params = p
+        self.cmat = as_c_material(self.material)
+        self.ctx = C.c_void_p()
+        check(self.lib.mcd_create(C.byref(p), C.byref(self.cmat), self.device, C.byref(self.ctx)))
+        lay = _lib.ScatLayout()
+        check(self.lib.mcd_scat_layout_get(self.ctx, C.byref(lay)), self.ctx)
+        self.row_words = int(lay.row_words)
+        self.word_of = list(lay.word_of)
+        self.tables = None
+        self.cap_el = self.cap_sc = 0
+        self.next_id = 0
+        self._pinned = {}
+
+    # ---- lifetime -----------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, 'ctx', None) is not None and self.ctx.value:
+            self.lib.mcd_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        check(rc, self.ctx)
+
+    # ---- tables -------------------------------------------------------------------------------
+    def table_build(self, slot, Es, Ws, shell_E=0.0, shell_n=0.0, stream=None):
+        Es, Ws = f32(Es), f32(Ws)
+        self._ck(self.lib.mcd_table_build(self.ctx, slot, fptr(Es), len(Es), fptr(Ws), len(Ws), shell_E, shell_n,
+                                          C.c_void_p(stream or 0)))
+
+    def table_upload(self, slot, Es, Ws, cdf):
+        Es, Ws, cdf = f32(Es), f32(Ws), f32(cdf)
+        assert cdf.shape == (len(Es), len(Ws) - 1), 'cdf must be nE x (nW-1)'
+        self._ck(self.lib.mcd_table_upload(self.ctx, slot, fptr(Es), len(Es), fptr(Ws), len(Ws), fptr(cdf)))
+
+    def table_download(self, slot):
+        nE, nW = C.c_uint32(), C.c_uint32()
+        self._ck(self.lib.mcd_table_shape(self.ctx, slot, C.byref(nE), C.byref(nW)))
+        out = np.empty((nE.value, nW.value - 1), dtype=np.float32)
+        self._ck(self.lib.mcd_table_download(self.ctx, slot, fptr(out)))
+        return out
+
+    # ---- runs ---------------------------------------------------------------------------------
+    def set_capacity(self, max_electrons, max_scat_rows=0):
+        if max_electrons != self.cap_el or max_scat_rows != self.cap_sc:
+            self._ck(self.lib.mcd_set_capacity(self.ctx, int(max_electrons), int(max_scat_rows)))
+            self.cap_el, self.cap_sc = max_electrons, max_scat_rows
+
+    def _host(self, key, nbytes, pinned):
+        """Reusable host staging buffer (pinned through torch when available)."""
+        buf = self._pinned.get(key)
+        if buf is None or buf.nbytes < nbytes:
+            if pinned:
+                import torch
+                t = torch.empty(max(nbytes, 1), dtype=torch.uint8, pin_memory=True)
+                buf = t.numpy()
+                self._pinned[key + '_t'] = t
+            else:
+                buf = np.empty(max(nbytes, 1), dtype=np.uint8)
+            self._pinned[key] = buf
+        return buf[:nbytes]
+
+    def launch(self, first_id, count, stream=None):
+        """Asynchronous mcd_run on `stream` (a raw cudaStream_t integer; None = default stream)."""
+        self._ck(self.lib.mcd_run(self.ctx, int(first_id), int(count), C.c_void_p(stream or 0)))
+
+    def sync(self, stream=None):
+        self._ck(self.lib.mcd_sync(self.ctx, C.c_void_p(stream or 0)))
+
+    def kernel_ms(self):
+        ms = C.c_float()
+        self._ck(self.lib.mcd_last_kernel_ms(self.ctx, C.byref(ms)))
+        return ms.value
+
+    def reset_stats(self, stream=None):
+        self._ck(self.lib.mcd_reset_stats(self.ctx, C.c_void_p(stream or 0)))
+
+    def counters(self):
+        c = _lib.Counters()
+        self._ck(self.lib.mcd_counters_get(self.ctx, C.byref(c)))
+        d = {k: int(getattr(c, k)) for k in ('electrons_done', 'events', 'double_records', 'scat_rows_stored',
+                                              'scat_rows_dropped', 'nan_clamped', 'select_exact')}
+        d['outcome'] = {n: int(c.outcome[i]) for i, n in enumerate(_lib.OUTCOMES)}
+        nch = self.cmat.n_shells + 3
+        d['channel'] = [int(c.channel[i]) for i in range(nch)]
+        return d
+
+    def histograms(self):
+        """Backscatter histograms (int64): final energy, exit polar angle from the surface normal, exit
+        azimuth, last interior depth; plus bin edges."""
+        h = np.empty(_lib.HIST_TOTAL, dtype=np.int64)
+        self._ck(self.lib.mcd_hist_get(self.ctx, h.ctypes.data_as(C.POINTER(C.c_int64))))
+        return self.split_hist(h)
+
+    def split_hist(self, h):
+        lo, hi, dm = C.c_double(), C.c_double(), C.c_double()
+        self._ck(self.lib.mcd_hist_ranges(self.ctx, C.byref(lo), C.byref(hi), C.byref(dm)))
+        a, b, c_ = _lib.HIST_E_BINS, _lib.HIST_POLAR_BINS, _lib.HIST_AZ_BINS
+        return {'energy': (h[:a], np.linspace(lo.value, hi.value, a + 1)),
+                'polar_deg': (h[a:a + b], np.linspace(0., 90., b + 1)),
+                'azimuth_deg': (h[a + b:a + b + c_], np.linspace(-180., 180., c_ + 1)),
+                'depth': (h[a + b + c_:], np.linspace(0., dm.value, _lib.HIST_DEPTH_BINS + 1))}
+
+    def stats_tensor(self):
+        """The device int64 histogram||counter block as a torch tensor (zero-copy), for the NCCL
+        all-reduce that is the path's only collective."""
+        import torch
+        ptr, n = C.c_void_p(), C.c_uint64()
+        self._ck(self.lib.mcd_stats_device_ptr(self.ctx, C.byref(ptr), C.byref(n)))
+
+        class _Wrap:
+            __cuda_array_interface__ = {'shape': (int(n.value),), 'typestr': '<i8', 'data': (int(ptr.value), False),
+                                        'version': 2}
+        return torch.as_tensor(_Wrap(), device='cuda:%d' % self.device)
+
+    def launch_info(self):
+        b, t, r, o = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        self._ck(self.lib.mcd_launch_info(self.ctx, C.byref(b), C.byref(t), C.byref(r), C.byref(o)))
+        return {'blocks': b.value, 'threads': t.value, 'regs': r.value, 'blocks_per_sm': o.value}
+
+    def drain(self, first_id, count, want_els=True, want_scats=True, pinned=False, stream=None):
+        """Copy the rows of the last run to host arrays."""
+        st = C.c_void_p(stream or 0)
+        n_els, n_sc = C.c_uint64(), C.c_uint64()
+        self._ck(self.lib.mcd_row_counts(self.ctx, C.byref(n_els), C.byref(n_sc)))
+        els = None
+        if want_els:
+            raw = self._host('els', count * 32, pinned)
+            self._ck(self.lib.mcd_drain_els(self.ctx, raw.ctypes.data_as(C.c_void_p), 0, count, st))
+            els = raw.view(_lib.EL_ROW_DTYPE)
+        scats = {}
+        nsc = int(n_sc.value)
+        words = None
+        if want_scats and self.row_words and self.cap_sc:
+            rawb = self._host('scats', nsc * self.row_words * 4, pinned)
+            if nsc:
+                self._ck(self.lib.mcd_drain_scats(self.ctx, rawb.ctypes.data_as(C.c_void_p), 0, nsc, st))
+            words = rawb.view(np.uint32).reshape(nsc, self.row_words)
+        self.sync(stream)
+        if words is not None:
+            scats['el'] = words[:, 0].astype(np.int64) + int(first_id)
+            scats['ev'] = (words[:, 1] & 0xffffff).astype(np.int32)
+            if self.word_of[0] >= 0:
+                scats['type'] = (words[:, 1] >> 24).astype(np.int8)
+            fl = words.view(np.float32)
+            names = {1: 'position', 2: 'pathl', 3: 'E', 4: 'E_loss', 5: 'pol_angle', 6: 'az_angle', 7: 'energy',
+                     8: 'direction'}
+            for b, nm in names.items():
+                w = self.word_of[b]
+                if w < 0:
+                    continue
+                if nm == 'position':
+                    scats['x'], scats['y'], scats['z'] = fl[:, w], fl[:, w + 1], fl[:, w + 2]
+                elif nm == 'direction':
+                    scats['direction'] = fl[:, w:w + 3]
+                else:
+                    scats[nm] = fl[:, w]
+        return els, scats
+
+    def run(self, count=None, first_id=None, max_scat_rows=None, pinned=False, stream=None, drain=True):
+        """Simulate `count` electrons (default inputPar['num_el']) with ids starting at `first_id`
+        (default: continue after the previous run) and return a RunResult."""
+        count = int(count if count is not None else self.inputPar['num_el'])
+        first_id = int(self.next_id if first_id is None else first_id)
+        if self.params.mode == _lib.MODE_DS and self.tables is None:
+            from .probTables import genTables
+            genTables(self.inputPar, engine=self)
+        auto = max_scat_rows is None
+        if auto:
+            max_scat_rows = 0
+            if self.row_words:
+                # a trajectory has at most maxScatt events; typical means are a few hundred
+                max_scat_rows = count * min(int(self.inputPar['maxScatt']), 512) + 65536
+        while True:
+            self.set_capacity(max(count, self.cap_el), max(max_scat_rows, self.cap_sc))
+            self.reset_stats(stream)
+            self.launch(first_id, count, stream)
+            self.sync(stream)
+            cnt = self.counters()
+            if not cnt['scat_rows_dropped']:
+                break
+            # Philox streams are keyed on the electron id, so re-running the batch reproduces it exactly
+            if not auto or self.cap_sc >= count * int(self.inputPar['maxScatt']):
+                raise _lib.MCDError(-5, '%d scats rows did not fit (capacity %d): raise max_scat_rows or run '
+                                    'fewer electrons per batch' % (cnt['scat_rows_dropped'], self.cap_sc))
+            max_scat_rows = min(2 * self.cap_sc, count * int(self.inputPar['maxScatt']))
+        self.next_id = max(self.next_id, first_id + count)
+        els, scats = self.drain(first_id, count, pinned=pinned, stream=stream) if drain else (None, {})
+        return RunResult(first_id, count, els, scats, cnt, self.kernel_ms())
+
+    # ---- unit hooks (parity tests) --------------------------------------------------------------
+    def test_sigmas(self, E):
+        E = f32(E)
+        nch = self.cmat.n_shells + 3
+        sig = np.empty((len(E), nch), np.float32)
+        mfp = np.empty(len(E), np.float32)
+        self._ck(self.lib.mcd_test_sigmas(self.ctx, fptr(E), len(E), fptr(sig), fptr(mfp)))
+        return sig, mfp
+
+    def test_select(self, sigma, u):
+        sigma, u = f32(sigma), f32(u)
+        pick = np.empty(len(u), np.int32)
+        path = np.empty(len(u), np.int32)
+        self._ck(self.lib.mcd_test_select(self.ctx, fptr(sigma), sigma.shape[1], fptr(u), len(u), iptr(pick), iptr(path)))
+        return pick, path
+
+    def test_ruth(self, E, u):
+        E, u = f32(E), f32(u)
+        c2, om = np.empty(len(E), np.float32), np.empty(len(E), np.float32)
+        self._ck(self.lib.mcd_test_ruth(self.ctx, fptr(E), fptr(u), len(E), fptr(c2), fptr(om)))
+        return c2, om
+
+    def test_bincoll(self, E, W):
+        E, W = f32(E), f32(W)
+        c2, om = np.empty(len(E), np.float32), np.empty(len(E), np.float32)
+        self._ck(self.lib.mcd_test_bincoll(self.ctx, fptr(E), fptr(W), len(E), fptr(c2), fptr(om)))
+        return c2, om
+
+    def test_rotate(self, d, y, c2, om, u_phi):
+        d, y, c2, om, u_phi = f32(d), f32(y), f32(c2), f32(om), f32(u_phi)
+        do, yo = np.empty_like(d), np.empty_like(y)
+        self._ck(self.lib.mcd_test_rotate(self.ctx, fptr(d), fptr(y), fptr(c2), fptr(om), fptr(u_phi), len(c2),
+                                          fptr(do), fptr(yo)))
+        return do, yo
+
+    def test_stopping(self, model, E):
+        E = f32(E)
+        sp = np.empty(len(E), np.float32)
+        self._ck(self.lib.mcd_test_stopping(self.ctx, _lib.BETHE[model], fptr(E), len(E), fptr(sp)))
+        return sp
+
+    def test_lookup(self, slot, E, u):
+        E, u = f32(E), f32(u)
+        W = np.empty(len(E), np.float32)
+        iE, jW = np.empty(len(E), np.int32), np.empty(len(E), np.int32)
+        self._ck(self.lib.mcd_test_lookup(self.ctx, slot, fptr(E), fptr(u), len(E), fptr(W), iptr(iE), iptr(jW)))
+        return W, iE, jW
+
+    def test_step(self, state, u):
+        state, u = f32(state), f32(u)
+        so = np.empty_like(state)
+        row = np.empty((len(state), 8), np.float32)
+        self._ck(self.lib.mcd_test_step(self.ctx, fptr(state), fptr(u), len(state), fptr(so), fptr(row)))
+        return so, row
+
+
+def philox(seed, el_id, ev):
+    lib = _lib.load()
+    raw = (C.c_uint32 * 4)()
+    u = (C.c_float * 4)()
+    check(lib.mcd_test_philox(int(seed), int(el_id), int(ev), raw, u))
+    return list(raw), list(u)

@@ -1,0 +1,115 @@
+"""CPU-only checks of the boundary: the C-ABI library loads and exports every symbol include/mcd.h
+declares, fails loudly without a GPU, and the host-side mirror of the reference interface
+(input parser, column contract, materials, table axis search) behaves like the reference."""
+import ctypes as C
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+
+
+@pytest.fixture(scope='module')
+def lib():
+    import __graft_entry__ as ge
+    from mcdiscrete_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        ge.build()
+    return _lib.load()
+
+
+def test_header_symbols_exported(lib):
+    from mcdiscrete_b200 import _lib
+    hdr = open(os.path.join(ROOT, 'include', 'mcd.h')).read()
+    declared = set(re.findall(r'^\s*(?:int|const char\*)\s+(mcd_\w+)\s*\(', hdr, flags=re.M))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.mcd_abi_version() == 1
+
+
+def test_struct_sizes_match_header(lib):
+    from mcdiscrete_b200 import _lib
+    assert C.sizeof(_lib.Material) == 8 + 6 * 8 + 2 * 8 * 8
+    assert C.sizeof(_lib.Params) == 7 * 8 + 8 + 4 * 4 + 4 * 4 + 8
+    assert _lib.EL_ROW_DTYPE.itemsize == 32
+    assert C.sizeof(_lib.Counters) == 8 * (2 + 5 + 5 + 11)
+
+
+def test_no_gpu_fails_loudly(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('a GPU is present')
+    from mcdiscrete_b200 import _lib
+    from mcdiscrete_b200.engine import Engine
+    n = C.c_int()
+    assert lib.mcd_device_count(C.byref(n)) == -3
+    with pytest.raises(_lib.MCDError) as ei:
+        Engine(dict(E0=2e4, Emin=1e4, material='Si', s_tilt=70., maxScatt=1000, mode='DS'))
+    assert 'no CPU fallback' in str(ei.value)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, 'mcdiscrete_b200')
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r'^\s*(import|from)\s+(mcd_oracle|oracle|ref_shim)', src, flags=re.M), f
+                assert 'oracle/' not in src or f.endswith(('.cu', '.cuh')), f   # comments in kernels may cite it
+
+
+def test_readInput_and_column_contract():
+    from mcdiscrete_b200.fileTools import readInput, thingsToSave, zipDict, flat_columns
+    ip = readInput(os.path.join(ROOT, 'tests', 'data', 'input.file'))
+    assert ip['num_el'] == 10 and isinstance(ip['num_el'], int)
+    assert ip['E0'] == 20000.0 and ip['material'] == 'Si' and ip['mode'] == 'DS'
+    assert ip['gen_tables'] is True and ip['diffMFP'] is False
+    assert ip['electron_output'] == ['outcome', 'final_E', 'final_dir', 'last_pos']
+    assert ip['scatter_output'] == ['type', 'position', 'energy']
+    assert ip['tol_W'] == 1e-7 and ip['maxScatt'] == 1000
+    t = thingsToSave(ip['scatter_output'])
+    t.addToList('position', [1., 2., 3.])
+    t.addToList('type', 'Ruth')
+    t.addToList('pathl', 5.)                      # not requested -> ignored (fileTools.py:219)
+    assert t.dict == {'type': ['Ruth'], 'position': {'x': [1.], 'y': [2.], 'z': [3.]}, 'energy': []}
+    merged = zipDict({}, t.dict)
+    assert list(merged) == ['type', 'energy', 'x', 'y', 'z']          # flattened keys move to the end
+    assert flat_columns(ip['scatter_output'], 'scats') == ['type', 'energy', 'x', 'y', 'z']
+    assert flat_columns(ip['electron_output'], 'els') == ['outcome', 'final_E', 'dx', 'dy', 'dz',
+                                                         'last_x', 'last_y', 'last_z']
+
+
+def test_material_matches_reference():
+    from mcdiscrete_b200.material import material
+    F = json.load(open(os.path.join(GOLD, 'formulas.json')))
+    for name, g in F.items():
+        m = material(name)
+        assert m.atnd == pytest.approx(g['atnd'], rel=1e-14)
+        assert m.fermi_e == pytest.approx(g['fermi_e'], rel=1e-14)
+        assert m.plasmon_e == pytest.approx(g['plasmon_e'], rel=1e-14)
+        assert m.channel_names[0] == 'Ruth' and m.channel_names[-1] == 'Quinn'
+
+
+@pytest.mark.parametrize('key', ['Si_15k_small', 'Al_500_small', 'Cu_10k_small', 'Si_10k_mid', 'Al_500_mid'])
+def test_host_axis_search_matches_reference(key):
+    """findWseries / findEseries (host side of the table build) against the reference's grids."""
+    from mcdiscrete_b200.material import material
+    from mcdiscrete_b200.probTables import probTable
+    ax = json.load(open(os.path.join(GOLD, 'table_axes.json')))[key]
+    ip = ax['input']
+    mat = material(ip['material'])
+    T = probTable('Moller', mat.params['name_val'], (ip['Emin'], ip['E0']), ip['tol_E'], ip['tol_W'], mat, Wc=ip['Wc'])
+    T.set_Ws(); T.set_Es()
+    assert [len(T.Es), len(T.Ws)] == ax['moller']
+    G = probTable('Gryzinski', mat.params['name_s'][-1], (ip['Emin'], ip['E0']), ip['tol_E'], ip['tol_W'], mat)
+    G.set_Ws(); G.set_Es()
+    assert [G.shell, len(G.Es), len(G.Ws)] == ax['gryz'][0]
+    if key.endswith('small'):
+        g = np.load(os.path.join(GOLD, 'tables_%s.npz' % key))
+        assert np.array_equal(T.Ws, g['moller_Ws']) and np.array_equal(T.Es, g['moller_Es'])
+        assert np.array_equal(G.Ws, g['gryz0_Ws']) and np.array_equal(G.Es, g['gryz0_Es'])
