@@ -40,8 +40,9 @@ struct mcd_ctx {
   mcd_el_row* els = nullptr;
   uint64_t max_el = 0;
   uint32_t* scats = nullptr;
-  uint64_t seg_cap = 0;
-  unsigned int* seg_count = nullptr;
+  uint32_t n_chunks = 0;                      // chunk pool size (MCD_CHUNK_ROWS rows each)
+  unsigned int* chunk_next = nullptr;
+  unsigned int* chunk_count = nullptr;
   unsigned long long* ticket = nullptr;
   unsigned long long* stats = nullptr;
   int n_blocks = 0;
@@ -49,7 +50,10 @@ struct mcd_ctx {
   // last run
   uint64_t last_count = 0;
   bool seg_cached = false;
-  std::vector<uint64_t> seg_prefix;           // n_blocks + 1
+  // stored rows as runs of consecutive pool rows: (first pool row, rows, prefix of rows before the run)
+  struct Run { uint64_t pool_row, rows, before; };
+  std::vector<Run> runs;
+  uint64_t rows_total = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
   std::string err;
@@ -303,15 +307,13 @@ int mcd_create(const mcd_params* p, const mcd_material* m, int device, mcd_ctx**
   c->n_blocks = c->li.blocks;
   if ((e = cudaMalloc(&c->ticket, sizeof(unsigned long long))) != cudaSuccess ||
       (e = cudaMalloc(&c->stats, kStatsWords * 8)) != cudaSuccess ||
-      (e = cudaMalloc(&c->seg_count, c->n_blocks * sizeof(unsigned int))) != cudaSuccess ||
+      (e = cudaMalloc(&c->chunk_next, sizeof(unsigned int))) != cudaSuccess ||
       (e = cudaMemset(c->stats, 0, kStatsWords * 8)) != cudaSuccess ||
-      (e = cudaMemset(c->seg_count, 0, c->n_blocks * sizeof(unsigned int))) != cudaSuccess ||
       (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess) {
     std::string msg = cudaGetErrorString(e);
     mcd_destroy(c);
     return fail(nullptr, MCD_ERR_CUDA, "context allocation: %s", msg.c_str());
   }
-  c->seg_prefix.assign(c->n_blocks + 1, 0);
   *out = c;
   return MCD_OK;
 }
@@ -320,7 +322,8 @@ int mcd_destroy(mcd_ctx* c) {
   if (!c) return MCD_OK;
   cudaSetDevice(c->device);
   for (auto& t : c->tab) free_table(t);
-  cudaFree(c->els); cudaFree(c->scats); cudaFree(c->seg_count); cudaFree(c->ticket); cudaFree(c->stats);
+  cudaFree(c->els); cudaFree(c->scats); cudaFree(c->chunk_next); cudaFree(c->chunk_count); cudaFree(c->ticket);
+  cudaFree(c->stats);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   delete c;
@@ -392,14 +395,18 @@ int mcd_set_capacity(mcd_ctx* c, uint64_t max_electrons, uint64_t max_scat_rows)
   if (max_electrons >> 32) return fail(c, MCD_ERR_INVALID, "at most 2^32-1 electrons per run (scats word 0 is 32 bit)");
   cudaFree(c->els); c->els = nullptr;
   cudaFree(c->scats); c->scats = nullptr;
-  c->max_el = 0; c->seg_cap = 0;
+  cudaFree(c->chunk_count); c->chunk_count = nullptr;
+  c->max_el = 0; c->n_chunks = 0;
   CU(c, cudaMalloc(&c->els, max_electrons * sizeof(mcd_el_row)));
   c->max_el = max_electrons;
   if (max_scat_rows && c->P.scat_row_words) {
-    const uint64_t cap = (max_scat_rows + c->n_blocks - 1) / c->n_blocks;
-    if (cap >> 32) return fail(c, MCD_ERR_INVALID, "scats segment too large");
-    CU(c, cudaMalloc(&c->scats, cap * c->n_blocks * (uint64_t)c->P.scat_row_words * 4));
-    c->seg_cap = cap;
+    // every warp of the resident grid may leave one partly filled chunk
+    const uint64_t warps = (uint64_t)c->n_blocks * (c->li.threads / 32);
+    const uint64_t nch = (max_scat_rows + MCD_CHUNK_ROWS - 1) / MCD_CHUNK_ROWS + warps;
+    if (nch >> 31) return fail(c, MCD_ERR_INVALID, "scats pool too large");
+    CU(c, cudaMalloc(&c->scats, nch * MCD_CHUNK_ROWS * (uint64_t)c->P.scat_row_words * 4));
+    CU(c, cudaMalloc(&c->chunk_count, nch * sizeof(unsigned int)));
+    c->n_chunks = (uint32_t)nch;
   }
   return MCD_OK;
 }
@@ -432,12 +439,14 @@ int mcd_run(mcd_ctx* c, uint64_t first_id, uint64_t count, void* stream) {
   }
   cudaStream_t s = (cudaStream_t)stream;
   CU(c, cudaMemsetAsync(c->ticket, 0, sizeof(unsigned long long), s));
-  CU(c, cudaMemsetAsync(c->seg_count, 0, c->n_blocks * sizeof(unsigned int), s));
+  CU(c, cudaMemsetAsync(c->chunk_next, 0, sizeof(unsigned int), s));
+  if (c->n_chunks) CU(c, cudaMemsetAsync(c->chunk_count, 0, (size_t)c->n_chunks * sizeof(unsigned int), s));
   DevOut O;
   O.els = c->els;
   O.scats = c->scats;
-  O.seg_cap_rows = c->seg_cap;
-  O.seg_count = c->seg_count;
+  O.n_chunks = c->n_chunks;
+  O.chunk_next = c->chunk_next;
+  O.chunk_count = c->chunk_count;
   O.ticket = c->ticket;
   O.stats = c->stats;
   CU(c, cudaEventRecord(c->ev0, s));
@@ -458,10 +467,24 @@ int mcd_sync(mcd_ctx* c, void* stream) {
 
 static int cache_segments(mcd_ctx* c) {
   if (c->seg_cached) return MCD_OK;
-  std::vector<unsigned int> cnt(c->n_blocks);
-  CU(c, cudaMemcpy(cnt.data(), c->seg_count, c->n_blocks * sizeof(unsigned int), cudaMemcpyDeviceToHost));
-  c->seg_prefix[0] = 0;
-  for (int b = 0; b < c->n_blocks; ++b) c->seg_prefix[b + 1] = c->seg_prefix[b] + (c->scats ? cnt[b] : 0u);
+  c->runs.clear();
+  c->rows_total = 0;
+  if (c->scats && c->n_chunks) {
+    unsigned int used = 0;
+    CU(c, cudaMemcpy(&used, c->chunk_next, sizeof used, cudaMemcpyDeviceToHost));
+    if (used > c->n_chunks) used = c->n_chunks;
+    std::vector<unsigned int> cnt(used);
+    if (used) CU(c, cudaMemcpy(cnt.data(), c->chunk_count, used * sizeof(unsigned int), cudaMemcpyDeviceToHost));
+    // merge consecutive chunks into runs: a run continues while the previous chunk is full
+    bool open = false;
+    for (unsigned int k = 0; k < used; ++k) {
+      if (cnt[k] == 0) { open = false; continue; }
+      if (open) c->runs.back().rows += cnt[k];
+      else c->runs.push_back({(uint64_t)k * MCD_CHUNK_ROWS, cnt[k], c->rows_total});
+      c->rows_total += cnt[k];
+      open = (cnt[k] == MCD_CHUNK_ROWS);
+    }
+  }
   c->seg_cached = true;
   return MCD_OK;
 }
@@ -472,7 +495,7 @@ int mcd_row_counts(mcd_ctx* c, uint64_t* n_els, uint64_t* n_scats) {
   rc = cache_segments(c);
   if (rc) return rc;
   if (n_els) *n_els = c->last_count;
-  if (n_scats) *n_scats = c->seg_prefix[c->n_blocks];
+  if (n_scats) *n_scats = c->rows_total;
   return MCD_OK;
 }
 
@@ -490,16 +513,22 @@ int mcd_drain_scats(mcd_ctx* c, uint32_t* host, uint64_t offset, uint64_t n, voi
   if (rc) return rc;
   rc = cache_segments(c);
   if (rc) return rc;
-  const uint64_t total = c->seg_prefix[c->n_blocks];
+  const uint64_t total = c->rows_total;
   if (!host || offset + n > total) return fail(c, MCD_ERR_INVALID, "scats range outside the stored rows");
   const uint64_t rw = (uint64_t)c->P.scat_row_words;
   uint64_t done = 0;
-  for (int b = 0; b < c->n_blocks && done < n; ++b) {
-    const uint64_t lo = c->seg_prefix[b], hi = c->seg_prefix[b + 1];
+  // first run containing `offset`
+  size_t lo = 0, hi = c->runs.size();
+  while (lo < hi) {
+    const size_t mid = (lo + hi) / 2;
+    if (c->runs[mid].before + c->runs[mid].rows <= offset) lo = mid + 1; else hi = mid;
+  }
+  for (size_t r = lo; r < c->runs.size() && done < n; ++r) {
+    const auto& R = c->runs[r];
     const uint64_t from = offset + done;
-    if (from >= hi || lo == hi) continue;
-    const uint64_t k = (hi - from < n - done) ? hi - from : n - done;
-    const uint32_t* src = c->scats + ((uint64_t)b * c->seg_cap + (from - lo)) * rw;
+    const uint64_t skip = from - R.before;
+    const uint64_t k = (R.rows - skip < n - done) ? R.rows - skip : n - done;
+    const uint32_t* src = c->scats + (R.pool_row + skip) * rw;
     CU(c, cudaMemcpyAsync(host + done * rw, src, k * rw * 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     done += k;
   }

@@ -7,9 +7,11 @@
 //    a global ticket (one warp-aggregated atomic per refill) so warps stay full until ids run out;
 //  * RNG = Philox4x32-10, key = seed, counter = (electron id, event index): results do not depend on
 //    which lane / block / GPU runs an electron;
-//  * outputs: one 32-byte els row per electron at index id - first_id; scats rows appended per block
-//    (shared-memory cursor, one warp-aggregated reservation per event) into that block's segment;
-//    backscatter histograms and counters accumulate in shared memory and are flushed once per block.
+//  * outputs: one 32-byte els row per electron at index id - first_id; scats rows are appended by each
+//    warp into chunks of MCD_CHUNK_ROWS rows that it takes from a global pool (ballot + popc give every
+//    lane its slot; the only atomic is one bump-allocation per chunk), so rows of one event are written
+//    contiguously and there is no per-event contention; backscatter histograms and counters accumulate
+//    in shared memory and are flushed once per block.
 #include "mcd_internal.h"
 
 namespace {
@@ -55,11 +57,11 @@ traj_kernel(const __grid_constant__ DevParams P, const DevOut O, const unsigned 
             const unsigned long long count) {
   __shared__ unsigned int s_hist[MCD_HIST_TOTAL];
   __shared__ unsigned long long s_cnt[kCntTotal];
-  __shared__ unsigned int s_cursor;
+  __shared__ unsigned long long s_rows[2];      // stored, dropped
 
   for (int i = threadIdx.x; i < MCD_HIST_TOTAL; i += kThreads) s_hist[i] = 0u;
   for (int i = threadIdx.x; i < kCntTotal; i += kThreads) s_cnt[i] = 0ull;
-  if (threadIdx.x == 0) s_cursor = 0u;
+  if (threadIdx.x < 2) s_rows[threadIdx.x] = 0ull;
   __syncthreads();
 
   const unsigned lane = threadIdx.x & 31u;
@@ -67,8 +69,9 @@ traj_kernel(const __grid_constant__ DevParams P, const DevOut O, const unsigned 
   const bool want_scats = (P.scat_row_words > 0) && (O.scats != nullptr);
   const bool want_hist = (P.flags & MCD_FLAG_HISTOGRAMS) != 0u;
   const bool want_chan = (P.flags & MCD_FLAG_CHANNEL_COUNTS) != 0u;
-  uint32_t* const seg = want_scats
-      ? O.scats + (size_t)blockIdx.x * (size_t)O.seg_cap_rows * (size_t)P.scat_row_words : nullptr;
+  int chunk = -1;                                // this warp's current chunk (warp-uniform)
+  unsigned int used = 0u;                        // rows already stored in it
+  unsigned int w_stored = 0u, w_dropped = 0u;    // warp-uniform tallies
 
   bool alive = false, exhausted = false;
   ElState e;
@@ -120,19 +123,36 @@ traj_kernel(const __grid_constant__ DevParams P, const DevOut O, const unsigned 
       }
     }
 
-    // ---- scats append: one reservation per warp per event ------------------------------------
+    // ---- scats append: warp-local slots in the warp's chunk; a new chunk when it is full --------
     if (want_scats) {
       const unsigned m = __ballot_sync(MCD_FULL_MASK, has_row);
       if (m) {
-        const int leader = __ffs(m) - 1;
-        unsigned int base = 0u;
-        if ((int)lane == leader) base = atomicAdd(&s_cursor, (unsigned int)__popc(m));
-        base = __shfl_sync(MCD_FULL_MASK, base, leader);
-        if (has_row) {
-          const unsigned long long r = (unsigned long long)base + (unsigned long long)__popc(m & lt);
-          if (r < O.seg_cap_rows)
-            store_scat_row(seg + r * (unsigned long long)P.scat_row_words, P.scat_mask, (uint32_t)rel_id, ev, row, e);
+        const unsigned k = (unsigned)__popc(m);
+        const unsigned rank = (unsigned)__popc(m & lt);
+        long long slot_row = -1;                                   // row index in the pool, -1 = dropped
+        if (chunk >= 0 && used + k <= MCD_CHUNK_ROWS) {
+          slot_row = (long long)chunk * MCD_CHUNK_ROWS + used + rank;
+          used += k;
+          w_stored += k;
+        } else {
+          const unsigned rem = (chunk >= 0) ? (MCD_CHUNK_ROWS - used) : 0u;
+          unsigned int nc = 0u;
+          if (lane == 0) {
+            if (chunk >= 0) O.chunk_count[chunk] = MCD_CHUNK_ROWS;   // old chunk gets filled below
+            nc = atomicAdd(O.chunk_next, 1u);
+          }
+          nc = __shfl_sync(MCD_FULL_MASK, nc, 0);
+          const bool got = nc < O.n_chunks;
+          if (rank < rem) slot_row = (long long)chunk * MCD_CHUNK_ROWS + used + rank;
+          else if (got) slot_row = (long long)nc * MCD_CHUNK_ROWS + (rank - rem);
+          w_stored += got ? k : rem;
+          w_dropped += got ? 0u : (k - rem);
+          chunk = got ? (int)nc : -1;
+          used = got ? (k - rem) : 0u;
         }
+        if (has_row && slot_row >= 0)
+          store_scat_row(O.scats + (size_t)slot_row * (size_t)P.scat_row_words, P.scat_mask, (uint32_t)rel_id, ev,
+                         row, e);
       }
     }
     if (has_row) {
@@ -170,7 +190,12 @@ traj_kernel(const __grid_constant__ DevParams P, const DevOut O, const unsigned 
     }
   }
 
-  // ---- flush block statistics ------------------------------------------------------------------
+  // ---- close this warp's chunk, flush block statistics ---------------------------------------------
+  if (want_scats && lane == 0) {
+    if (chunk >= 0) O.chunk_count[chunk] = used;
+    if (w_stored) atomicAdd(&s_rows[0], (unsigned long long)w_stored);
+    if (w_dropped) atomicAdd(&s_rows[1], (unsigned long long)w_dropped);
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < MCD_HIST_TOTAL; i += kThreads) {
     const unsigned int v = s_hist[i];
@@ -184,11 +209,8 @@ traj_kernel(const __grid_constant__ DevParams P, const DevOut O, const unsigned 
     for (int i = 0; i < 5; ++i) if (s_cnt[kCntOutcome + i]) atomicAdd(cnt + 2 + i, s_cnt[kCntOutcome + i]);
     if (s_cnt[kCntDouble]) atomicAdd(cnt + 7, s_cnt[kCntDouble]);
     if (want_scats) {
-      const unsigned long long appended = s_cursor;
-      const unsigned long long stored = appended < O.seg_cap_rows ? appended : O.seg_cap_rows;
-      O.seg_count[blockIdx.x] = (unsigned int)stored;
-      atomicAdd(cnt + 8, stored);
-      if (appended > stored) atomicAdd(cnt + 9, appended - stored);
+      if (s_rows[0]) atomicAdd(cnt + 8, s_rows[0]);
+      if (s_rows[1]) atomicAdd(cnt + 9, s_rows[1]);
     }
     if (s_cnt[kCntNan]) atomicAdd(cnt + 10, s_cnt[kCntNan]);
     if (s_cnt[kCntExact]) atomicAdd(cnt + 11, s_cnt[kCntExact]);
@@ -241,7 +263,6 @@ cudaError_t mcd_launch_traj(const DevParams& P, const DevOut& O, unsigned long l
   TrajLaunchInfo li;
   cudaError_t err = mcd_traj_max_blocks(P, sm_count, &li);
   if (err != cudaSuccess) return err;
-  // the grid is always the full resident set: scats segments are sized per block of this grid
   if (info) *info = li;
   k<<<li.blocks, kThreads, 0, stream>>>(P, O, first_id, count);
   return cudaGetLastError();

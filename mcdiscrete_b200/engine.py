@@ -151,7 +151,10 @@ class Engine:
             self.cap_el, self.cap_sc = max_electrons, max_scat_rows
 
     def _host(self, key, nbytes, pinned):
-        """Reusable host staging buffer (pinned through torch when available)."""
+        """Host destination for a drain: a fresh array, or with pinned=True a REUSED page-locked staging
+        buffer (the returned rows are then only valid until the next drain)."""
+        if not pinned:
+            return np.empty(max(nbytes, 1), dtype=np.uint8)[:nbytes]
         buf = self._pinned.get(key)
         if buf is None or buf.nbytes < nbytes:
             if pinned:

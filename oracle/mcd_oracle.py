@@ -461,8 +461,9 @@ def philox4x32_10(counter, key):
 
 
 def u01(x):
-    """32 random bits -> float32-exact uniform in (0,1): ((x >> 8) + 0.5) * 2^-24."""
-    return ((x >> 8) + 0.5) * (1.0 / 16777216.0)
+    """32 random bits -> uniform in (0,1) that is EXACT in float32: ((x >> 9) + 0.5) * 2^-23
+    (23 random bits plus the half-offset fill the 24-bit significand; never 0 or 1)."""
+    return ((x >> 9) + 0.5) * (1.0 / 8388608.0)
 
 
 def event_uniforms(seed, el_id, ev_idx):
