@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the per-electron trajectory loop (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload = "C2"): BASELINE.json configs[1] -- Si, E0 = 20 keV, DS mode
+(Rutherford + Moller + Gryzinski + Quinn), default table tolerances (tol_E 1e-4, tol_W 1e-7), 70 deg tilt,
+num_el = 1e6 per GPU; Emin = 10 keV and maxScatt = 1000 from the reference's inputFile/input.file (BASELINE.json
+leaves them open).  One step = one pass of the trajectory kernel over 1e6 fresh electrons of the synthetic
+pencil beam (ids never repeat across steps), histograms + counters fused, one els row per electron.
+Weak scaling: every rank simulates its own 1e6 electrons (disjoint Philox streams); the only collective is the
+int64 all-reduce of the histogram||counter block (NCCL).
+
+Printed JSON: `value` = electrons/s with tables resident in HBM, device-timed (CUDA events, max over
+ranks); `e2e` = the same through the public call Engine.run() with pinned HOST output buffers, i.e.
+including per step the launch-parameter upload, the D2H copy of every els row, histograms and counters;
+`roofline` for the trajectory kernel against the MEASURED FP32 / MUFU peaks of this GPU; `cpu_baseline` =
+the oracle's C restatement of the reference loop on the host cores (bounded sample).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NUM_EL = 1_000_000
+WORKLOAD = dict(num_el=NUM_EL, E0=20000., Emin=10000., material='Si', s_tilt=70., thickness=3e6,
+                elastic='Ruth_vanilla', mode='DS', Bethe_model='classical', diffMFP=False, gen_tables=True,
+                tol_E=1e-4, tol_W=1e-7, maxScatt=1000, Wc=10.,
+                electron_output=['outcome', 'final_E', 'final_dir', 'last_pos'], scatter_output=[], seed=12345)
+# algorithmic work per DS event: F = 181 + 24 S flops, M = 11 + 3 S MUFU ops, S = core shells
+N_SHELLS = 3
+FLOPS_PER_EVENT = 181 + 24 * N_SHELLS
+MUFU_PER_EVENT = 11 + 3 * N_SHELLS
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(',')]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15 and len(r) >= 9] or [r for _, r in self.rows if len(r) >= 9]
+        if not rows:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
+        sm = sorted(float(r[1]) for r in rows)
+        reasons = set()
+        for r in rows:
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(rows[0][2]), 'reasons': sorted(reasons),
+                'samples': len(rows), 'power_w_max': max(float(r[3]) for r in rows)}
+
+
+def cpu_sample(n_el, nthreads, tables=None):
+    """The oracle's C restatement of the reference loop on the host cores; returns (el/s, events/s, dt, tables)."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import mcd_oracle as orc
+    import mcd_oracle_cbind as oc
+    if tables is None:
+        tables = orc.gen_tables(dict(WORKLOAD, tol_E=1e-3, tol_W=1e-5))
+    oc.run(WORKLOAD, 10 ** 9, 64, 1, tables, nthreads=nthreads)           # warm-up (library load, page-in)
+    t0 = time.time()
+    r = oc.run(WORKLOAD, 10 ** 9 + 1000, n_el, 1, tables, nthreads=nthreads)
+    dt = time.time() - t0
+    return n_el / dt, float(r['n_ev'].sum()) / dt, dt, tables
+
+
+def run_reference(args, rank):
+    """`--impl reference`: the reference's CPU implementation of the path on the host cores.  The reference is
+    pure Python and /root/reference does not exist on the GPU box, so this is the oracle port: the C restatement
+    (all host threads) is the timed arm; the Python restatement, which mirrors the reference's per-event object
+    structure and runs at the reference's own speed (~100-250 us/event/core), is reported beside it."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_el = 20000
+    tables = None
+    vals, evs = [], []
+    for s in range(args.warmup + args.steps):
+        el_s, ev_s, dt, tables = cpu_sample(n_el, cores, tables)
+        if s >= args.warmup:
+            vals.append(el_s)
+            evs.append(ev_s)
+    v = sum(vals) / len(vals)
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import mcd_oracle as orc
+    t0 = time.time()
+    py = orc.run_electrons(WORKLOAD, 5 * 10 ** 9, 24, 1, tables)
+    dtp = time.time() - t0
+    sample = ('%d electrons per step of workload C2 (Si 20 keV DS tilt 70 Emin 10 keV), oracle C restatement, %d '
+              'threads; tables at tol_E 1e-3 / tol_W 1e-5 (numpy oracle; lookup cost does not depend on table size)'
+              % (n_el, cores))
+    print(json.dumps({
+        'impl': 'reference', 'metric': 'electron trajectories/s', 'value': v, 'unit': 'electrons/s', 'n_gpus': 0,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * n_el / v, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'events_per_s': sum(evs) / len(evs),
+        'config': {'workload': 'C2', 'material': 'Si', 'E0_eV': 20000, 'Emin_eV': 10000, 'mode': 'DS',
+                   's_tilt_deg': 70, 'num_el_per_step': n_el, 'maxScatt': 1000},
+        'cpu_baseline': {'value': v, 'unit': 'electrons/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'python_port': {'value': 24 / dtp, 'unit': 'electrons/s', 'cores': 1,
+                        'note': 'pure-Python restatement with the reference\'s per-event structure, 24 electrons'},
+        'e2e': {'value': v, 'unit': 'electrons/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours')
+    ap.add_argument('--num-el', type=int, default=NUM_EL)
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+
+    rank = int(os.environ.get('RANK', 0))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    if args.impl == 'reference':
+        return run_reference(args, rank)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: mcdiscrete_b200 has no CPU fallback')
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    from mcdiscrete_b200 import _lib
+    from mcdiscrete_b200.engine import Engine
+    from mcdiscrete_b200.probTables import genTables
+    from mcdiscrete_b200.distributed import allreduce_stats, rank_range
+
+    n_el = args.num_el
+    ip = dict(WORKLOAD, num_el=n_el)
+    eng = Engine(ip, device=local)
+    t0 = time.time()
+    tabs = genTables(ip, engine=eng)
+    torch.cuda.synchronize()
+    t_tables = time.time() - t0
+    table_bytes = sum(4 * len(T.Es) * (len(T.Ws) - 1) for T in [tabs['Moller']] + tabs['Gryz'])
+    eng.set_capacity(n_el, 0)
+    stream = torch.cuda.current_stream().cuda_stream
+    stats = eng.stats_tensor()
+
+    # measured compute roofs of this GPU (FMA and MUFU chains)
+    import ctypes as C
+    f32p, mufu, mhz = C.c_float(), C.c_float(), C.c_float()
+    _lib.check(eng.lib.mcd_measure_peaks(local, C.byref(f32p), C.byref(mufu), C.byref(mhz)))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    step_id = [0]
+
+    def first_id():
+        # fresh electrons every step, disjoint across ranks
+        fid = (step_id[0] * world + rank) * n_el
+        step_id[0] += 1
+        return fid
+
+    def device_step():
+        eng.reset_stats(stream)
+        eng.launch(first_id(), n_el, stream)
+        if world > 1:
+            allreduce_stats(stats)
+
+    # ---- device-timed throughput ------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        device_step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    kernel_ms = []
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tw0 = time.time()
+    ev0.record()
+    for _ in range(args.steps):
+        device_step()
+    ev1.record()
+    barrier()
+    tw1 = time.time()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop(tw0, tw1)
+    tmax = torch.tensor([ms], device='cuda')
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms = float(tmax.item())
+    cnt = eng.counters()                      # of the last step (summed over ranks when world > 1)
+    events_per_step = cnt['events']           # whole job
+    electrons_per_step = cnt['electrons_done']
+    assert electrons_per_step == n_el * world, (electrons_per_step, n_el, world)
+    value = electrons_per_step * args.steps / (ms * 1e-3)
+    events_s = events_per_step * args.steps / (ms * 1e-3)
+
+    # kernel-only duration (CUDA events around the trajectory kernel inside mcd_run, on its launch stream)
+    for _ in range(args.steps):
+        eng.reset_stats(stream)
+        eng.launch(first_id(), n_el, stream)
+        eng.sync(stream)
+        kernel_ms.append(eng.kernel_ms())
+    k_ms = sum(kernel_ms) / len(kernel_ms)
+    ev_local = eng.counters()['events']
+    ev_rate = ev_local / (k_ms * 1e-3)        # this rank's kernel
+    fp32_ach = ev_rate * FLOPS_PER_EVENT / 1e12
+    mufu_ach = ev_rate * MUFU_PER_EVENT / 1e12
+    fp32_frac, mufu_frac = fp32_ach / f32p.value, mufu_ach / mufu.value
+    traffic = None
+    prof = os.path.join(ROOT, 'profiles', 'r1_traj_kernel_summary.json')
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get('dram_bytes_per_launch')
+        except Exception:
+            traffic = None
+    bound = 'mufu' if mufu_frac >= fp32_frac else 'fp32'
+    roofline = {'bound': bound,
+                'achieved': mufu_ach if bound == 'mufu' else fp32_ach,
+                'peak': mufu.value if bound == 'mufu' else f32p.value,
+                'unit': 'Ttranscendental/s' if bound == 'mufu' else 'TFLOP/s',
+                'frac': max(mufu_frac, fp32_frac), 'traffic': traffic,
+                'kernel': 'traj_kernel<3,DS>', 'kernel_ms': k_ms, 'events_per_launch': ev_local,
+                'fp32': {'achieved_tflops': fp32_ach, 'peak_tflops': f32p.value, 'frac': fp32_frac,
+                         'flops_per_event': FLOPS_PER_EVENT},
+                'mufu': {'achieved_tops': mufu_ach, 'peak_tops': mufu.value, 'frac': mufu_frac,
+                         'ops_per_event': MUFU_PER_EVENT},
+                'peak_source': 'measured on this GPU by mcd_measure_peaks (FFMA / MUFU.EX2 dependent chains); '
+                               'MEASURED_PEAKS.json has no FP32/MUFU figure',
+                'hbm': {'table_bytes_resident': table_bytes, 'peak_gbs_measured': 6547.2}}
+
+    # ---- end to end through the public API with pinned host outputs ------------------------------------------
+    h2d = C.sizeof(_lib.Params) + 1024      # launch parameter block: there are no per-step input arrays
+    d2h = n_el * 32 + 8 * (_lib.HIST_TOTAL + C.sizeof(_lib.Counters) // 8)
+    for _ in range(2):
+        eng.run(count=n_el, first_id=first_id(), pinned=True, stream=stream)
+    barrier()
+    t0 = time.time()
+    for _ in range(args.steps):
+        r = eng.run(count=n_el, first_id=first_id(), pinned=True, stream=stream)
+        h = eng.histograms()
+        if world > 1:
+            allreduce_stats(stats)
+    barrier()
+    dt = time.time() - t0
+    tdt = torch.tensor([dt], device='cuda')
+    if world > 1:
+        dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
+    e2e = n_el * world * args.steps / float(tdt.item())
+    eta = float((r.outcome == 1).mean())
+
+    if rank == 0:
+        out = {
+            'metric': 'electron trajectories/s', 'value': value, 'unit': 'electrons/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'events_per_s': events_s, 'events_per_electron': events_per_step / max(electrons_per_step, 1),
+            'config': {'workload': 'C2', 'material': 'Si', 'E0_eV': 20000, 'Emin_eV': 10000, 'mode': 'DS',
+                       's_tilt_deg': 70, 'tol_E': 1e-4, 'tol_W': 1e-7, 'maxScatt': 1000, 'num_el_per_gpu': n_el,
+                       'outputs': 'one els row per electron + fused backscatter histograms + counters',
+                       'cache': 'inputs larger than L2 (inverse-CDF tables %.2f GB resident in HBM)' % (table_bytes / 1e9),
+                       'parallelism': 'electron ids partitioned across %d GPU(s); int64 histogram all-reduce' % world},
+            'e2e': {'value': e2e, 'unit': 'electrons/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+            'gpu_launches': args.steps,
+            'clocks': clocks,
+            'roofline': roofline,
+            'setup': {'tables_s': t_tables, 'table_shapes': {'Moller': [len(tabs['Moller'].Es), len(tabs['Moller'].Ws)],
+                                                             'Gryz0': [len(tabs['Gryz'][0].Es), len(tabs['Gryz'][0].Ws)]},
+                      'launch': eng.launch_info(), 'sm_mhz_est_from_mufu': mhz.value},
+            'physics': {'backscatter_fraction': eta, 'select_exact_frac': cnt['select_exact'] / max(events_per_step, 1),
+                        'nan_clamped': cnt['nan_clamped']},
+        }
+        if not args.no_cpu and world == 1:
+            cores = os.cpu_count() or 1
+            el_s, ev_s, dtc, _ = cpu_sample(40000, cores)
+            out['cpu_baseline'] = {'value': el_s, 'unit': 'electrons/s', 'cores': cores, 'kind': 'port',
+                                   'events_per_s': ev_s,
+                                   'sample': '40000 electrons of workload C2 (%.1f s), oracle C restatement of the '
+                                             'reference loop, %d threads; tables at tol_E 1e-3 / tol_W 1e-5' % (dtc, cores)}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -197,6 +197,11 @@ int mcd_last_kernel_ms(mcd_ctx* ctx, float* ms);
 /* Launch geometry of the trajectory kernel (blocks, threads, registers/thread, blocks/SM). */
 int mcd_launch_info(mcd_ctx* ctx, int* blocks, int* threads, int* regs, int* blocks_per_sm);
 
+/* ---- roofline denominators ---------------------------------------------------------------------- */
+/* Measure the FP32 FMA peak (TFLOP/s, FMA = 2 flop) and the MUFU/XU peak (1e12 transcendental op/s) of
+ * `device` with dependent-chain micro-kernels; sm_mhz_est = the SM clock implied by the MUFU rate. */
+int mcd_measure_peaks(int device, float* fp32_tflops, float* mufu_tops, float* sm_mhz_est);
+
 /* ---- unit hooks (injected uniforms; all arrays are HOST pointers, n vectors) --------------- */
 /* sigma_out: n x (S+3) in sigma insertion order, cm^2; mfp_out: total mean free path in Angstrom. */
 int mcd_test_sigmas(mcd_ctx* ctx, const float* E, uint64_t n, float* sigma_out, float* mfp_out);

@@ -1,0 +1,140 @@
+"""Statistical parity of full runs (BASELINE.json north_star): backscatter coefficient within 3 sigma,
+two-sample KS p > 0.01 on energy / exit angle / depth of the backscattered electrons, against INDEPENDENT
+samples from the oracle (different Philox seed), plus the reference's own stochastic checks
+(tests/testThings.py: channel frequencies at E0, Rutherford / Moller polar angles, uniform azimuth)
+re-expressed on the GPU scats rows."""
+import math
+import os
+
+import numpy as np
+import pytest
+from scipy import stats
+
+import mcd_oracle as o
+import mcd_oracle_cbind as oc
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+P_MIN = 0.01
+
+
+def _engine(ip, tabs=None, **kw):
+    from mcdiscrete_b200.engine import Engine
+    eng = Engine(ip, device=0, **kw)
+    if tabs is not None:
+        eng.table_upload(0, tabs['Moller'].Es, tabs['Moller'].Ws, tabs['Moller'].table)
+        eng.table_upload(1, tabs['Gryz'][0].Es, tabs['Gryz'][0].Ws, tabs['Gryz'][0].table)
+        eng.tables = tabs
+    return eng
+
+
+def _compare(res, ref, n_gpu, n_ref):
+    out = res.outcome
+    eta_g, eta_r = (out == 1).mean(), (ref['outcome'] == 1).mean()
+    sig = math.sqrt(eta_g * (1 - eta_g) / n_gpu + eta_r * (1 - eta_r) / n_ref)
+    assert abs(eta_g - eta_r) < 3 * sig, 'eta gpu %.4f vs oracle %.4f (3 sigma = %.4f)' % (eta_g, eta_r, 3 * sig)
+    b, rb = out == 1, ref['outcome'] == 1
+    checks = {
+        'final_E': (res.els['final_E'][b], ref['final_E'][rb]),
+        'exit_polar': (np.degrees(np.arccos(np.clip(-res.els['dz'][b], -1, 1))),
+                       np.degrees(np.arccos(np.clip(-ref['final_dir'][rb, 2], -1, 1)))),
+        'exit_azimuth': (np.arctan2(res.els['dy'][b], res.els['dx'][b]),
+                         np.arctan2(ref['final_dir'][rb, 1], ref['final_dir'][rb, 0])),
+        'depth_last_z': (res.els['last_z'][b], ref['last_pos'][rb, 2]),
+        'abs_last_z': (res.els['last_z'][out == 0], ref['last_pos'][ref['outcome'] == 0, 2]),
+    }
+    ps = {}
+    for k, (a, c) in checks.items():
+        if len(a) < 50 or len(c) < 50:
+            continue
+        ps[k] = stats.ks_2samp(a.astype(np.float64), c).pvalue
+    bad = {k: p for k, p in ps.items() if p <= P_MIN}
+    assert not bad, 'KS failures: %s (all: %s)' % (bad, ps)
+    return eta_g, eta_r, ps
+
+
+@pytest.mark.parametrize('name,E0,Emin,tilt', [('Si', 20000., 10000., 70.), ('Cu', 20000., 10000., 70.),
+                                               ('Au', 30000., 15000., 0.)])
+def test_full_run_statistics_DS(name, E0, Emin, tilt):
+    ip = dict(E0=E0, Emin=Emin, material=name, s_tilt=tilt, thickness=3e6, mode='DS', maxScatt=4000, Wc=10.,
+              tol_E=1e-3, tol_W=1e-4, electron_output=['outcome', 'final_E', 'final_dir', 'last_pos'],
+              scatter_output=[], seed=777)
+    tabs = o.gen_tables(ip, strict=False)
+    n_gpu, n_ref = 200000, 40000
+    eng = _engine(ip, tabs)
+    res = eng.run(count=n_gpu, first_id=0)
+    ref = oc.run(ip, 0, n_ref, 4242, tabs, nthreads=os.cpu_count() or 1)      # independent stream
+    eta_g, eta_r, ps = _compare(res, ref, n_gpu, n_ref)
+    # events per electron: mean within 1 %
+    ev_g = res.counters['events'] / n_gpu
+    assert abs(ev_g - ref['n_ev'].mean()) < 0.02 * ref['n_ev'].mean()
+    # same seed: the overwhelming majority of trajectories is identical to the float64 oracle
+    same = oc.run(ip, 0, 20000, 777, tabs, nthreads=os.cpu_count() or 1)
+    agree = (res.outcome[:20000] == same['outcome']).mean()
+    assert agree > 0.97, agree
+    # the fused histograms are consistent with the rows
+    h = eng.histograms()
+    bks = res.outcome == 1
+    assert h['energy'][0].sum() == bks.sum() == h['polar_deg'][0].sum() == h['depth'][0].sum()
+    hist_E, _ = np.histogram(res.els['final_E'][bks], bins=h['energy'][1])
+    assert np.abs(hist_E - h['energy'][0]).sum() <= 2e-3 * bks.sum()          # bin-edge rounding only
+    eng.close()
+
+
+@pytest.mark.parametrize('model', ['classical', 'JL', 'explicit'])
+def test_full_run_statistics_cont(model):
+    ip = dict(E0=20000., Emin=500., material='Al', s_tilt=70., thickness=3e6, mode='cont', Bethe_model=model,
+              maxScatt=100000, Wc=10., electron_output=['outcome', 'final_E', 'final_dir', 'last_pos'],
+              scatter_output=[], seed=31)
+    n_gpu, n_ref = 200000, 40000
+    eng = _engine(ip)
+    res = eng.run(count=n_gpu, first_id=0)
+    ref = oc.run(ip, 0, n_ref, 99, nthreads=os.cpu_count() or 1)
+    _compare(res, ref, n_gpu, n_ref)
+    eng.close()
+
+
+def test_reference_stochastic_checks_on_scats():
+    """tests/testThings.py re-expressed: Al, 20 keV, tilt 0, DS (testInput.file), on the scats rows."""
+    ip = dict(E0=20000., Emin=15000., material='Al', s_tilt=0., thickness=3e6, mode='DS', maxScatt=10000, Wc=10.,
+              tol_E=1e-3, tol_W=1e-4, electron_output=['outcome'],
+              scatter_output=['type', 'pol_angle', 'E', 'E_loss', 'az_angle'], seed=5)
+    tabs = o.gen_tables(ip, strict=False)
+    eng = _engine(ip, tabs)
+    n = 20000
+    res = eng.run(count=n, first_id=0)
+    sc = res.scats
+    mat = o.Material('Al')
+    names = mat.channel_names
+    # Test_crossSection (testThings.py:321-387): channel frequencies at E == E0 vs sigma_i / sum(sigma)
+    at_E0 = sc['E'] == np.float32(20000.)
+    sig = np.array(o.sigmas_ds(20000., mat, 10.))
+    obs = np.bincount(sc['type'][at_E0], minlength=len(names)).astype(float)
+    exp = sig / sig.sum() * obs.sum()
+    keep = exp > 5
+    chi2 = ((obs[keep] - exp[keep]) ** 2 / exp[keep]).sum() + (obs[~keep].sum() - exp[~keep].sum()) ** 2 / max(exp[~keep].sum(), 1e-9)
+    assert chi2 < stats.chi2.ppf(0.999, keep.sum()), (chi2, obs, exp)
+    # TestPolarProb_Ruth_E0 (:393-434): Rutherford polar angle at E0 vs the analytic inverse CDF
+    ruth0 = at_E0 & (sc['type'] == 0)
+    a = o.alpha(20000., mat.Z)
+    theta = 2 * np.arccos(np.sqrt(np.clip(sc['pol_angle'][ruth0].astype(np.float64), 0, 1)))
+    cdf = lambda th: (1 + a) * np.sin(th / 2) ** 2 / (a + np.sin(th / 2) ** 2)      # u(theta) from c2 = 1 - a u/(1+a-u)
+    assert stats.kstest(theta, cdf).pvalue > P_MIN
+    # TestAzimProb_Ruth (:491-522): azimuth 2*halfPhi uniform on [0, 360)
+    az = 2 * np.degrees(sc['az_angle'][sc['type'] == 0].astype(np.float64))
+    assert stats.kstest(az[:200000], stats.uniform(0, 360).cdf).pvalue > P_MIN
+    # TestPolarProb_Moller_E0 (:529-639): W at E0 follows the Moller dCS between Wc and (E0-Ef)/2
+    mol0 = at_E0 & (sc['type'] == 1)
+    W = sc['E_loss'][mol0].astype(np.float64)
+    Wg = np.geomspace(10., (20000. - mat.fermi_e) / 2, 200001)
+    f = o.moller_dCS(20000., Wg, mat.n_val)
+    F = np.concatenate([[0], np.cumsum((f[1:] + f[:-1]) / 2 * np.diff(Wg))])
+    F /= F[-1]
+    # the table returns the LOWER bin edge (scattering.py:92), i.e. a discretised W: compare CDFs on the grid
+    Ws = tabs['Moller'].Ws.astype(np.float64)
+    emp = np.searchsorted(np.sort(W), Ws, side='right') / len(W)
+    theo = np.interp(np.concatenate([Ws[1:], Ws[-1:]]), Wg, F)
+    assert np.abs(emp - theo).max() < 1.63 / math.sqrt(len(W)) + 2e-3          # KS critical value at p = 0.01
+    c2 = sc['pol_angle'][mol0].astype(np.float64)
+    assert np.allclose(c2, 0.5 * (np.sqrt(1 - W / 20000.) + 1), rtol=2e-6)      # binaryCollModel
+    eng.close()
