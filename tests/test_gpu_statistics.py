@@ -28,14 +28,17 @@ def _engine(ip, tabs=None, **kw):
     return eng
 
 
-def _compare(res, ref, n_gpu, n_ref):
+def _ks_table(res, ref):
+    """Two-sample KS p-values, backscattered (and absorbed-depth) distributions, GPU rows vs oracle rows.
+    final_E is a comb of exact ties (E0 - k*E_plasmon - table losses) that the GPU holds in float32 and the
+    oracle in float64: a +-0.05 eV jitter on both samples breaks the ties so that rounding a tooth by 1e-3 eV
+    does not register as a distribution shift."""
     out = res.outcome
-    eta_g, eta_r = (out == 1).mean(), (ref['outcome'] == 1).mean()
-    sig = math.sqrt(eta_g * (1 - eta_g) / n_gpu + eta_r * (1 - eta_r) / n_ref)
-    assert abs(eta_g - eta_r) < 3 * sig, 'eta gpu %.4f vs oracle %.4f (3 sigma = %.4f)' % (eta_g, eta_r, 3 * sig)
     b, rb = out == 1, ref['outcome'] == 1
+    rng = np.random.default_rng(0)
+    jit = lambda x: np.asarray(x, np.float64) + rng.uniform(-0.05, 0.05, len(x))
     checks = {
-        'final_E': (res.els['final_E'][b], ref['final_E'][rb]),
+        'final_E': (jit(res.els['final_E'][b]), jit(ref['final_E'][rb])),
         'exit_polar': (np.degrees(np.arccos(np.clip(-res.els['dz'][b], -1, 1))),
                        np.degrees(np.arccos(np.clip(-ref['final_dir'][rb, 2], -1, 1)))),
         'exit_azimuth': (np.arctan2(res.els['dy'][b], res.els['dx'][b]),
@@ -43,12 +46,24 @@ def _compare(res, ref, n_gpu, n_ref):
         'depth_last_z': (res.els['last_z'][b], ref['last_pos'][rb, 2]),
         'abs_last_z': (res.els['last_z'][out == 0], ref['last_pos'][ref['outcome'] == 0, 2]),
     }
-    ps = {}
-    for k, (a, c) in checks.items():
-        if len(a) < 50 or len(c) < 50:
-            continue
-        ps[k] = stats.ks_2samp(a.astype(np.float64), c).pvalue
+    return {k: stats.ks_2samp(np.asarray(a, np.float64), np.asarray(c, np.float64)).pvalue
+            for k, (a, c) in checks.items() if len(a) >= 50 and len(c) >= 50}
+
+
+def _compare(res, ref, n_gpu, n_ref, second_sample=None):
+    """eta within 3 sigma and KS p > 0.01 against an independent oracle sample.  With 5 distributions x 6
+    configurations a true-null p <= 0.01 turns up by chance about once in 4 suite runs, so a failing
+    distribution is re-tested against a SECOND independent oracle sample and must pass there (a real
+    discrepancy fails both; a chance failure repeats with probability 1e-2)."""
+    out = res.outcome
+    eta_g, eta_r = (out == 1).mean(), (ref['outcome'] == 1).mean()
+    sig = math.sqrt(eta_g * (1 - eta_g) / n_gpu + eta_r * (1 - eta_r) / n_ref)
+    assert abs(eta_g - eta_r) < 3 * sig, 'eta gpu %.4f vs oracle %.4f (3 sigma = %.4f)' % (eta_g, eta_r, 3 * sig)
+    ps = _ks_table(res, ref)
     bad = {k: p for k, p in ps.items() if p <= P_MIN}
+    if bad and second_sample is not None:
+        ps2 = _ks_table(res, second_sample())
+        bad = {k: (p, ps2[k]) for k, p in bad.items() if ps2[k] <= P_MIN}
     assert not bad, 'KS failures: %s (all: %s)' % (bad, ps)
     return eta_g, eta_r, ps
 
@@ -64,14 +79,15 @@ def test_full_run_statistics_DS(name, E0, Emin, tilt):
     eng = _engine(ip, tabs)
     res = eng.run(count=n_gpu, first_id=0)
     ref = oc.run(ip, 0, n_ref, 4242, tabs, nthreads=os.cpu_count() or 1)      # independent stream
-    eta_g, eta_r, ps = _compare(res, ref, n_gpu, n_ref)
+    eta_g, eta_r, ps = _compare(res, ref, n_gpu, n_ref,
+                                lambda: oc.run(ip, 0, n_ref, 2024, tabs, nthreads=os.cpu_count() or 1))
     # events per electron: mean within 1 %
     ev_g = res.counters['events'] / n_gpu
     assert abs(ev_g - ref['n_ev'].mean()) < 0.02 * ref['n_ev'].mean()
     # same seed: the overwhelming majority of trajectories is identical to the float64 oracle
     same = oc.run(ip, 0, 20000, 777, tabs, nthreads=os.cpu_count() or 1)
     agree = (res.outcome[:20000] == same['outcome']).mean()
-    assert agree > 0.97, agree
+    assert agree > 0.999, agree
     # the fused histograms are consistent with the rows
     h = eng.histograms()
     bks = res.outcome == 1
@@ -90,7 +106,7 @@ def test_full_run_statistics_cont(model):
     eng = _engine(ip)
     res = eng.run(count=n_gpu, first_id=0)
     ref = oc.run(ip, 0, n_ref, 99, nthreads=os.cpu_count() or 1)
-    _compare(res, ref, n_gpu, n_ref)
+    _compare(res, ref, n_gpu, n_ref, lambda: oc.run(ip, 0, n_ref, 2024, nthreads=os.cpu_count() or 1))
     eng.close()
 
 
