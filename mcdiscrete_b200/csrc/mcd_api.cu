@@ -24,6 +24,7 @@ struct HostTable {
   float* Es = nullptr;
   float* Ws = nullptr;
   int* nvalid = nullptr;
+  uint32_t* guide = nullptr;
   uint32_t nE = 0, nW = 0;
 };
 
@@ -101,6 +102,7 @@ void build_dev_params(mcd_ctx* c) {
   m.cR = (float)(5.21e-21 * Z * Z * 1e6 * 4.0 * M_PI * scale / aZ);
   m.cM = (float)(mt.n_val * kPiEFour * scale);
   m.Wc = (float)p.Wc;
+  m.invWc = (float)(1.0 / p.Wc);
   const double b = mt.plasmon_e / mt.fermi_e;
   m.cQ = (float)(mt.plasmon_e * 1e-10 / (2.0 * kBohrM));
   m.Kq = (float)((sqrt(1.0 + b) - 1.0) / b);
@@ -179,13 +181,13 @@ void refresh_tables(mcd_ctx* c) {
   for (int s = 0; s < MCD_MAX_TABLES; ++s) {
     DevTable& d = c->P.tab[s];
     const HostTable& h = c->tab[s];
-    d.cdf = h.cdf; d.Es = h.Es; d.Ws = h.Ws; d.nvalid = h.nvalid;
+    d.cdf = h.cdf; d.Es = h.Es; d.Ws = h.Ws; d.nvalid = h.nvalid; d.guide = h.guide;
     d.nE = (int)h.nE; d.nW = (int)h.nW;
   }
 }
 
 void free_table(HostTable& h) {
-  cudaFree(h.cdf); cudaFree(h.Es); cudaFree(h.Ws); cudaFree(h.nvalid);
+  cudaFree(h.cdf); cudaFree(h.Es); cudaFree(h.Ws); cudaFree(h.nvalid); cudaFree(h.guide);
   h = HostTable();
 }
 
@@ -198,6 +200,7 @@ int alloc_table(mcd_ctx* c, int slot, const float* Es, uint32_t nE, const float*
   CU(c, cudaMalloc(&h.Es, nE * sizeof(float)));
   CU(c, cudaMalloc(&h.Ws, nW * sizeof(float)));
   CU(c, cudaMalloc(&h.nvalid, nE * sizeof(int)));
+  CU(c, cudaMalloc(&h.guide, (size_t)nE * (MCD_GUIDE + 1) * sizeof(uint32_t)));
   CU(c, cudaMemcpy(h.Es, Es, nE * sizeof(float), cudaMemcpyHostToDevice));
   CU(c, cudaMemcpy(h.Ws, Ws, nW * sizeof(float), cudaMemcpyHostToDevice));
   h.nE = nE;
@@ -352,6 +355,7 @@ int mcd_table_build(mcd_ctx* c, int slot, const float* Es, uint32_t nE, const fl
   CU(c, scratch.alloc((uint64_t)blocks * (nW - 1)));
   a.scratch = scratch.p;
   CU(c, mcd_launch_table_build(a, blocks, (cudaStream_t)stream));
+  CU(c, mcd_launch_table_guide(h.cdf, (int)nE, (int)nW, h.nvalid, h.guide, (cudaStream_t)stream));
   CU(c, cudaStreamSynchronize((cudaStream_t)stream));
   return MCD_OK;
 }
@@ -366,6 +370,7 @@ int mcd_table_upload(mcd_ctx* c, int slot, const float* Es, uint32_t nE, const f
   HostTable& h = c->tab[slot];
   CU(c, cudaMemcpy(h.cdf, cdf, (size_t)nE * (nW - 1) * sizeof(float), cudaMemcpyHostToDevice));
   CU(c, mcd_launch_table_nvalid(h.cdf, (int)nE, (int)nW, h.nvalid, 0));
+  CU(c, mcd_launch_table_guide(h.cdf, (int)nE, (int)nW, h.nvalid, h.guide, 0));
   CU(c, cudaDeviceSynchronize());
   return MCD_OK;
 }

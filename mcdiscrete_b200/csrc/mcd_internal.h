@@ -30,6 +30,8 @@ cudaError_t mcd_traj_max_blocks(const DevParams& P, int sm_count, TrajLaunchInfo
 // mcd_tables.cu
 cudaError_t mcd_launch_table_build(const TableBuildArgs& a, int blocks, cudaStream_t stream);
 cudaError_t mcd_launch_table_nvalid(const float* cdf, int nE, int nW, int* nvalid, cudaStream_t stream);
+cudaError_t mcd_launch_table_guide(const float* cdf, int nE, int nW, const int* nvalid, uint32_t* guide,
+                                   cudaStream_t stream);
 
 // mcd_unit.cu
 cudaError_t mcd_launch_test_sigmas(const DevParams& P, const float* E, uint64_t n, float* sig, float* mfp,

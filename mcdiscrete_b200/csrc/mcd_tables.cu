@@ -140,7 +140,31 @@ __global__ void table_nvalid_kernel(const float* __restrict__ cdf, int nE, int n
   nvalid[row] = lo;
 }
 
+// guide[row][g] = bisect_left(row[0:nvalid], g / MCD_GUIDE) for g = 0..MCD_GUIDE: brackets every lookup
+// (table_lookup in mcd_device.cuh) without changing its result.
+__global__ void table_guide_kernel(const float* __restrict__ cdf, int nE, int nW, const int* __restrict__ nvalid,
+                                   uint32_t* __restrict__ guide) {
+  const int row = blockIdx.x;
+  const float* r = cdf + (size_t)row * (size_t)(nW - 1);
+  const int nv = nvalid[row];
+  for (int g = threadIdx.x; g <= MCD_GUIDE; g += blockDim.x) {
+    const float t = (float)g * (1.0f / (float)MCD_GUIDE);
+    int lo = 0, hi = nv;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (r[mid] < t) lo = mid + 1; else hi = mid;
+    }
+    guide[(size_t)row * (MCD_GUIDE + 1) + g] = (uint32_t)lo;
+  }
+}
+
 }  // namespace
+
+cudaError_t mcd_launch_table_guide(const float* cdf, int nE, int nW, const int* nvalid, uint32_t* guide,
+                                   cudaStream_t stream) {
+  table_guide_kernel<<<nE, 256, 0, stream>>>(cdf, nE, nW, nvalid, guide);
+  return cudaGetLastError();
+}
 
 cudaError_t mcd_launch_table_build(const TableBuildArgs& a, int blocks, cudaStream_t stream) {
   table_build_kernel<<<blocks, kTB, 0, stream>>>(a);

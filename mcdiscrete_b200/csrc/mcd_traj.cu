@@ -52,7 +52,7 @@ __device__ __forceinline__ void store_scat_row(uint32_t* __restrict__ dst, uint3
 }
 
 template <int S, int MODE>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 traj_kernel(const __grid_constant__ DevParams P, const DevOut O, const unsigned long long first_id,
             const unsigned long long count) {
   __shared__ unsigned int s_hist[MCD_HIST_TOTAL];

@@ -10,10 +10,11 @@ constexpr int kT = 128;
 template <int S>
 __device__ void sigmas_insertion(const DevParams& P, float E, float* out /* S+3 */, float* tot) {
   const DevMat& m = P.m;
+  const float invE = f_rcp(E);
   out[0] = s_ruth(m, E);
-  out[1] = s_moller(m, E);
-  for (int k = 0; k < S; ++k) out[2 + m.gShell[k]] = s_gryz(E, m.gE[k], m.gInvE[k], m.gC[k]);
-  out[2 + S] = s_quinn(m, E);
+  out[1] = s_moller(m, E, invE);
+  for (int k = 0; k < S; ++k) out[2 + m.gShell[k]] = s_gryz(E, invE, m.gE[k], m.gInvE[k], m.gC[k]);
+  out[2 + S] = s_quinn(m, E, invE);
   // same association as the trajectory kernel: slot order Ruth, Quinn, Moller, Gryz slots
   float t = out[0] + out[2 + S];
   t += out[1];
@@ -76,7 +77,7 @@ __global__ void k_ruth(const __grid_constant__ DevParams P, const float* E, cons
                        float* om) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float o = ruth_om(P.m, E[i], u[i]);
+  const float o = ruth_om(P.m, f_rcp(E[i]), u[i]);
   om[i] = o;
   c2[i] = 1.0f - o;
 }
@@ -90,7 +91,7 @@ __global__ void k_bincoll(const __grid_constant__ DevParams P, const float* E, c
     c2[i] = __int_as_float(0x7fc00000);
     return;
   }
-  const float o = bincoll_om(E[i], W[i]);
+  const float o = bincoll_om(f_rcp(E[i]), W[i]);
   om[i] = o;
   c2[i] = 1.0f - o;
 }
