@@ -88,6 +88,39 @@ double gryz_sigma_host(double E, double Es, double ns) {          // crossSectio
          (1. + (2. * (1. - (1. / (2. * U))) / 3. * log(2.7 + sqrt(U - 1.)))) / (E * Es);
 }
 
+// sigma formulas in float64 (crossSections.py:37-58, 183-208, 247-284) for the host-side order proof
+double ruth_sigma_host(double E, double Z) {
+  const double a = 3.4 * pow(Z, 0.666667) / E, Ek = E * 1e-3, r = (Ek + 511.) / (Ek + 1024.);
+  return 5.21e-21 * (Z * Z / (Ek * Ek)) * r * r * (4. * M_PI) / (a * (1. + a));
+}
+double moller_sigma_host(double E, double Wc, double nfree) {
+  if (E <= Wc) return 0.;
+  const double eps = Wc / E;
+  return nfree * kPiEFour / (E * E) * (1. / eps - 1. / (1. - eps) + log(eps / (1. - eps)));
+}
+double quinn_sigma_host(double E, double Epl, double Ef, double n) {
+  const double a = E / Ef, b = Epl / Ef;
+  return Epl * log((sqrt(1. + b) - 1.) / (sqrt(a) - sqrt(a - b))) / (2. * kBohrM * E) / n * 1e4;
+}
+
+// The kernel evaluates the channels in slot order Ruth, Quinn, Moller, Gryzinski[order[]].  If that is the
+// descending-sigma order (what pickFromSigmas' sort produces, scattering.py:48) with a 0.1 % margin at every
+// one of 4096 log-spaced energies of [Emin, E0], the per-event order check is skipped.
+int order_is_static(const mcd_params& p, const mcd_material& mt, const int* order) {
+  const int n = 4096;
+  for (int i = 0; i < n; ++i) {
+    const double E = p.Emin * pow(p.E0 / p.Emin, (double)i / (n - 1));
+    double s[MCD_MAX_CHANNELS];
+    s[0] = ruth_sigma_host(E, mt.Z);
+    s[1] = quinn_sigma_host(E, mt.plasmon_e, mt.fermi_e, mt.atnd);
+    s[2] = moller_sigma_host(E, p.Wc, mt.n_val);
+    for (int k = 0; k < mt.n_shells; ++k) s[3 + k] = gryz_sigma_host(E, mt.shell_E[order[k]], mt.shell_n[order[k]]);
+    for (int k = 1; k < mt.n_shells + 3; ++k)
+      if (!(s[k - 1] > 1.001 * s[k]) || s[k] <= 0.0) return 0;
+  }
+  return 1;
+}
+
 void build_dev_params(mcd_ctx* c) {
   const mcd_params& p = c->par;
   const mcd_material& mt = c->mat;
@@ -155,6 +188,11 @@ void build_dev_params(mcd_ctx* c) {
   P.gryz_per_shell = (p.gryz_table_mode == MCD_GRYZ_PER_SHELL);
   P.seed_lo = (uint32_t)p.seed;
   P.seed_hi = (uint32_t)(p.seed >> 32);
+  for (int r = 0; r < 10; ++r) {                                    // Philox key schedule
+    P.pkey[2 * r] = P.seed_lo + (uint32_t)r * 0x9E3779B9u;
+    P.pkey[2 * r + 1] = P.seed_hi + (uint32_t)r * 0xBB67AE85u;
+  }
+  P.order_static = (p.mode == MCD_MODE_DS) ? order_is_static(p, mt, order) : 0;
   P.scat_mask = p.scat_mask;
   P.flags = p.flags;
   // histogram axes: energy [Emin,E0], depth [0, 2R], R = E0 / S_Bethe,classical(E0)
@@ -191,7 +229,8 @@ void free_table(HostTable& h) {
   h = HostTable();
 }
 
-int alloc_table(mcd_ctx* c, int slot, const float* Es, uint32_t nE, const float* Ws, uint32_t nW) {
+int alloc_table(mcd_ctx* c, int slot, const float* Es, uint32_t nE, const float* Ws, uint32_t nW,
+                double es_start_hint) {
   if (slot < 0 || slot >= MCD_MAX_TABLES) return fail(c, MCD_ERR_INVALID, "table slot %d out of range", slot);
   if (nE < 2 || nW < 3 || !Es || !Ws) return fail(c, MCD_ERR_INVALID, "table axes too small (nE=%u nW=%u)", nE, nW);
   HostTable& h = c->tab[slot];
@@ -208,7 +247,20 @@ int alloc_table(mcd_ctx* c, int slot, const float* Es, uint32_t nE, const float*
   refresh_tables(c);
   DevTable& d = c->P.tab[slot];
   d.E_lo = Es[0];
+  d.E_hi = Es[nE - 1];
   d.inv_dE = (float)((double)(nE - 1) / ((double)Es[nE - 1] - (double)Es[0]));
+  // Is Es exactly numpy.linspace(start, stop, nE, dtype=float32) for the (start, stop) the reference would use
+  // (probTables.py:137-142, 364-379)?  Then the device regenerates grid values instead of loading them.
+  d.es_analytic = 0;
+  const double starts[2] = {c->par.Emin, es_start_hint};
+  for (int k = 0; k < 2 && !d.es_analytic; ++k) {
+    const double start = starts[k], stop = c->par.E0;
+    if (!(start > 0) || !(stop > start)) continue;
+    const double step = (stop - start) / (double)(nE - 1);
+    bool same = ((float)stop == Es[nE - 1]);
+    for (uint32_t i = 0; same && i + 1 < nE; ++i) same = ((float)((double)i * step + start) == Es[i]);
+    if (same) { d.es_analytic = 1; d.es_start = start; d.es_step = step; }
+  }
   return MCD_OK;
 }
 
@@ -338,7 +390,7 @@ int mcd_table_build(mcd_ctx* c, int slot, const float* Es, uint32_t nE, const fl
                     double shell_E, double shell_n, void* stream) {
   int rc = need_ctx(c);
   if (rc) return rc;
-  rc = alloc_table(c, slot, Es, nE, Ws, nW);
+  rc = alloc_table(c, slot, Es, nE, Ws, nW, shell_E);
   if (rc) return rc;
   HostTable& h = c->tab[slot];
   TableBuildArgs a;
@@ -365,7 +417,8 @@ int mcd_table_upload(mcd_ctx* c, int slot, const float* Es, uint32_t nE, const f
   int rc = need_ctx(c);
   if (rc) return rc;
   if (!cdf) return fail(c, MCD_ERR_INVALID, "null cdf");
-  rc = alloc_table(c, slot, Es, nE, Ws, nW);
+  // Gryzinski grids may start at the shell's binding energy = Ws[0] (probTables.py:125,137-142)
+  rc = alloc_table(c, slot, Es, nE, Ws, nW, (double)Ws[0]);
   if (rc) return rc;
   HostTable& h = c->tab[slot];
   CU(c, cudaMemcpy(h.cdf, cdf, (size_t)nE * (nW - 1) * sizeof(float), cudaMemcpyHostToDevice));

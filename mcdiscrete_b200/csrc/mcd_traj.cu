@@ -33,10 +33,10 @@ __device__ __forceinline__ unsigned lanemask_lt() {
 }
 
 __device__ __forceinline__ void store_scat_row(uint32_t* __restrict__ dst, uint32_t mask, uint32_t rel_id,
-                                               uint32_t ev, const EventRow& r, const ElState& e) {
+                                               uint32_t ev, int channel, const EventRow& r, const ElState& e) {
   int w = 0;
   dst[w++] = rel_id;
-  dst[w++] = (ev & 0xffffffu) | ((uint32_t)r.channel << 24);
+  dst[w++] = (ev & 0xffffffu) | ((uint32_t)channel << 24);
   if (mask & MCD_SC_POSITION) {
     dst[w++] = __float_as_uint(r.px); dst[w++] = __float_as_uint(r.py); dst[w++] = __float_as_uint(r.pz);
   }
@@ -109,19 +109,24 @@ traj_kernel(const __grid_constant__ DevParams P, const DevOut O, const unsigned 
     EventRow row;
     OutcomeSnap sn;
     row.flags = 0;
+    EventMid mid;
+    mid.tab = -1;
+    mid.invE = 0.f; mid.W = 0.f; mid.om = 0.f;
+    float4 u = make_float4(0.5f, 0.5f, 0.5f, 0.5f);
     if (alive) {
-      if ((long long)ev >= (long long)P.maxScatt) {              // singleScatter.py:19-23
+      if (ev >= (uint32_t)P.maxScatt) {                          // singleScatter.py:19-23
         outcome = MCD_OUT_LONG;
         snap(sn, e);
       } else {
-        const float4 u = event_uniforms(P, first_id + rel_id, ev);
-        if (MODE == MCD_MODE_DS) ds_event<S>(P, e, u, row, sn);
+        u = event_uniforms(P, first_id + rel_id, ev);
+        if (MODE == MCD_MODE_DS) ds_phase_a<S>(P, e, u, row, sn, mid);
         else cont_event(P, e, u, row, sn);
         has_row = true;
-        outcome = row.outcome;
         ++my_events;
       }
     }
+    if (MODE == MCD_MODE_DS && has_row) ds_phase_b(P, e, u, row, sn, mid);
+    if (has_row) outcome = row.outcome;
 
     // ---- scats append: warp-local slots in the warp's chunk; a new chunk when it is full --------
     if (want_scats) {
@@ -152,13 +157,15 @@ traj_kernel(const __grid_constant__ DevParams P, const DevOut O, const unsigned 
         }
         if (has_row && slot_row >= 0)
           store_scat_row(O.scats + (size_t)slot_row * (size_t)P.scat_row_words, P.scat_mask, (uint32_t)rel_id, ev,
-                         row, e);
+                         slot_channel(P.m, row.slot), row, e);
       }
     }
     if (has_row) {
-      if (want_chan) atomicAdd(&s_cnt[kCntChan + row.channel], 1ull);
-      if (row.flags & MCD_EVF_NANCLAMP) atomicAdd(&s_cnt[kCntNan], 1ull);
-      if (row.flags & MCD_EVF_EXACT) atomicAdd(&s_cnt[kCntExact], 1ull);
+      if (want_chan) atomicAdd(&s_cnt[kCntChan + slot_channel(P.m, row.slot)], 1ull);
+      if (row.flags & (MCD_EVF_NANCLAMP | MCD_EVF_EXACT)) {
+        if (row.flags & MCD_EVF_NANCLAMP) atomicAdd(&s_cnt[kCntNan], 1ull);
+        if (row.flags & MCD_EVF_EXACT) atomicAdd(&s_cnt[kCntExact], 1ull);
+      }
       ++ev;
     }
 

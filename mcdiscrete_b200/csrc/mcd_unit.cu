@@ -124,37 +124,48 @@ __global__ void k_lookup(const __grid_constant__ DevParams P, int slot, const fl
 }
 
 template <int S>
-__device__ void step_one(const DevParams& P, ElState& e, float4 u, EventRow& row, OutcomeSnap& sn) {
-  if (P.mode == MCD_MODE_DS) ds_event<S>(P, e, u, row, sn);
-  else cont_event(P, e, u, row, sn);
+__device__ void step_one(const DevParams& P, bool on, ElState& e, float4 u, EventRow& row, OutcomeSnap& sn) {
+  if (!on) return;
+  if (P.mode == MCD_MODE_DS) {
+    EventMid mid;
+    ds_phase_a<S>(P, e, u, row, sn, mid);
+    ds_phase_b(P, e, u, row, sn, mid);
+  } else {
+    cont_event(P, e, u, row, sn);
+  }
 }
 
 __global__ void k_step(const __grid_constant__ DevParams P, const float* st, const float* uu, uint64_t n,
                        float* st_out, float* row_out) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  const bool on = i < n;
   ElState e;
-  const float* s = st + 10 * i;
-  e.E = s[0]; e.x = s[1]; e.y = s[2]; e.z = s[3]; e.dx = s[4]; e.dy = s[5]; e.dz = s[6];
-  e.yx = s[7]; e.yy = s[8]; e.yz = s[9];
-  const float4 u = make_float4(uu[4 * i], uu[4 * i + 1], uu[4 * i + 2], uu[4 * i + 3]);
+  e.E = P.E0; e.x = e.y = e.z = 0.f; e.dx = 0.f; e.dy = 0.f; e.dz = 1.f; e.yx = 0.f; e.yy = 1.f; e.yz = 0.f;
+  float4 u = make_float4(0.5f, 0.5f, 0.5f, 0.5f);
+  if (on) {
+    const float* s = st + 10 * i;
+    e.E = s[0]; e.x = s[1]; e.y = s[2]; e.z = s[3]; e.dx = s[4]; e.dy = s[5]; e.dz = s[6];
+    e.yx = s[7]; e.yy = s[8]; e.yz = s[9];
+    u = make_float4(uu[4 * i], uu[4 * i + 1], uu[4 * i + 2], uu[4 * i + 3]);
+  }
   EventRow row;
   OutcomeSnap sn;
   switch (P.m.nshell) {
-    case 1: step_one<1>(P, e, u, row, sn); break;
-    case 2: step_one<2>(P, e, u, row, sn); break;
-    case 3: step_one<3>(P, e, u, row, sn); break;
-    case 4: step_one<4>(P, e, u, row, sn); break;
-    case 5: step_one<5>(P, e, u, row, sn); break;
-    case 6: step_one<6>(P, e, u, row, sn); break;
-    case 7: step_one<7>(P, e, u, row, sn); break;
-    default: step_one<8>(P, e, u, row, sn); break;
+    case 1: step_one<1>(P, on, e, u, row, sn); break;
+    case 2: step_one<2>(P, on, e, u, row, sn); break;
+    case 3: step_one<3>(P, on, e, u, row, sn); break;
+    case 4: step_one<4>(P, on, e, u, row, sn); break;
+    case 5: step_one<5>(P, on, e, u, row, sn); break;
+    case 6: step_one<6>(P, on, e, u, row, sn); break;
+    case 7: step_one<7>(P, on, e, u, row, sn); break;
+    default: step_one<8>(P, on, e, u, row, sn); break;
   }
+  if (!on) return;
   float* o = st_out + 10 * i;
   o[0] = e.E; o[1] = e.x; o[2] = e.y; o[3] = e.z; o[4] = e.dx; o[5] = e.dy; o[6] = e.dz;
   o[7] = e.yx; o[8] = e.yy; o[9] = e.yz;
   float* r = row_out + 8 * i;
-  r[0] = (float)row.channel; r[1] = row.pathl; r[2] = row.E_loss; r[3] = row.c2; r[4] = row.halfPhi;
+  r[0] = (float)slot_channel(P.m, row.slot); r[1] = row.pathl; r[2] = row.E_loss; r[3] = row.c2; r[4] = row.halfPhi;
   r[5] = row.energy; r[6] = (float)row.outcome; r[7] = (float)row.flags;
 }
 

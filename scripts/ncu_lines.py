@@ -18,7 +18,7 @@ I = hdr.index('Instructions Executed'); S = hdr.index('# Samples'); L = hdr.inde
 T = hdr.index('Thread Instructions Executed')
 ti = sum(num(r[I]) for _, r in lines); ts = sum(num(r[S]) for _, r in lines)
 print('total warp instructions %.4g, samples %d' % (ti, ts))
-lines.sort(key=lambda fr: -num(fr[1][S]))
+lines.sort(key=lambda fr: -num(fr[1][I if (len(sys.argv) > 3 and sys.argv[3] == "inst") else S]))
 print('%7s %7s %7s %5s  %s' % ('inst%', 'samp%', 'longsb%', 'thr', 'line'))
 for f, r in lines[:top]:
     print('%6.2f%% %6.2f%% %6.2f%% %5.1f  %s:%s  %s' % (100 * num(r[I]) / ti, 100 * num(r[S]) / ts, 100 * num(r[L]) / max(num(r[S]), 1),
