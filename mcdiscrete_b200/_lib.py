@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libmcd.so')
+LIB_PATH = os.environ.get('MCD_LIB') or os.path.join(_HERE, 'libmcd.so')     # MCD_LIB: tuning experiments only
 
 MAX_SHELLS = 8
 MAX_CHANNELS = MAX_SHELLS + 3

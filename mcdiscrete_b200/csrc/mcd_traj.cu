@@ -12,11 +12,16 @@
 //    lane its slot; the only atomic is one bump-allocation per chunk), so rows of one event are written
 //    contiguously and there is no per-event contention; backscatter histograms and counters accumulate
 //    in shared memory and are flushed once per block.
+#include <stdlib.h>
+
 #include "mcd_internal.h"
 
 namespace {
 
 constexpr int kThreads = 256;
+#ifndef MCD_MIN_BLOCKS
+#define MCD_MIN_BLOCKS 4          // resident blocks per SM the register allocation is held to (64 regs)
+#endif
 constexpr int kCntOutcome = 0;       // 5
 constexpr int kCntEvents = 5;
 constexpr int kCntDone = 6;
@@ -52,7 +57,7 @@ __device__ __forceinline__ void store_scat_row(uint32_t* __restrict__ dst, uint3
 }
 
 template <int S, int MODE>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, MCD_MIN_BLOCKS)
 traj_kernel(const __grid_constant__ DevParams P, const DevOut O, const unsigned long long first_id,
             const unsigned long long count) {
   __shared__ unsigned int s_hist[MCD_HIST_TOTAL];
@@ -256,6 +261,10 @@ cudaError_t mcd_traj_max_blocks(const DevParams& P, int sm_count, TrajLaunchInfo
   err = cudaFuncGetAttributes(&fa, k);
   if (err != cudaSuccess) return err;
   if (per_sm < 1) per_sm = 1;
+  if (const char* env = getenv("MCD_BLOCKS_PER_SM")) {      // tuning knob: fewer resident blocks than the maximum
+    const int v = atoi(env);
+    if (v >= 1 && v < per_sm) per_sm = v;
+  }
   info->blocks = per_sm * sm_count;
   info->threads = kThreads;
   info->regs = fa.numRegs;

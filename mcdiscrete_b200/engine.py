@@ -23,11 +23,71 @@ def _mask(names, bits):
     return m
 
 
+class ScatRows:
+    """The drained scats rows: a (n_rows, row_words) uint32 array plus lazily evaluated columns.
+
+    Column access is dict-like (``sc['energy']``, ``'x' in sc``, ``sc.keys()``).  Float columns are strided VIEWS
+    into the packed rows (no copy); 'el' (absolute electron id), 'ev' (event index) and 'type' (channel index in
+    sigma insertion order) are decoded on first use."""
+
+    _FLOAT = {1: 'position', 2: 'pathl', 3: 'E', 4: 'E_loss', 5: 'pol_angle', 6: 'az_angle', 7: 'energy',
+              8: 'direction'}
+
+    def __init__(self, words, word_of, first_id):
+        self.words, self.word_of, self.first_id = words, word_of, int(first_id)
+        self._cache = {}
+        self._names = ['el', 'ev']
+        if word_of[0] >= 0:
+            self._names.append('type')
+        for b, nm in self._FLOAT.items():
+            if word_of[b] >= 0:
+                self._names += ['x', 'y', 'z'] if nm == 'position' else [nm]
+
+    def __len__(self):
+        return len(self.words)
+
+    def __bool__(self):
+        return True
+
+    def keys(self):
+        return list(self._names)
+
+    def __contains__(self, k):
+        return k in self._names
+
+    def items(self):
+        return [(k, self[k]) for k in self._names]
+
+    def __getitem__(self, k):
+        if k in self._cache:
+            return self._cache[k]
+        if k not in self._names:
+            raise KeyError(k)
+        w = self.words
+        fl = w.view(np.float32)
+        if k == 'el':
+            v = w[:, 0].astype(np.int64) + self.first_id
+        elif k == 'ev':
+            v = (w[:, 1] & 0xffffff).astype(np.int32)
+        elif k == 'type':
+            v = (w[:, 1] >> 24).astype(np.int8)
+        elif k in ('x', 'y', 'z'):
+            v = fl[:, self.word_of[1] + 'xyz'.index(k)]
+        elif k == 'direction':
+            v = fl[:, self.word_of[8]:self.word_of[8] + 3]
+        else:
+            b = [b for b, nm in self._FLOAT.items() if nm == k][0]
+            v = fl[:, self.word_of[b]]
+        self._cache[k] = v
+        return v
+
+
 class RunResult:
     """Columnar output of one run.
 
     els   : structured array (code, final_E, dx, dy, dz, last_x, last_y, last_z), row i = electron first_id+i
-    scats : dict of column arrays in append order, with 'el' (absolute electron id) and 'ev' (event index)
+    scats : ScatRows (dict-like columns in append order, with 'el' = absolute electron id and 'ev' = event
+            index) or {} when no scatter_output was requested
     """
 
     def __init__(self, first_id, count, els, scats, counters, kernel_ms):
@@ -44,10 +104,11 @@ class RunResult:
 
     def sorted_scats(self):
         """scats columns regrouped per electron in event order (the reference's row order)."""
-        if not self.scats:
+        if not len(self.scats):
             return self.scats
-        order = np.lexsort((self.scats['ev'], self.scats['el']))
-        return {k: v[order] for k, v in self.scats.items()}
+        w = self.scats.words
+        order = np.lexsort((w[:, 1] & 0xffffff, w[:, 0]))
+        return ScatRows(w[order], self.scats.word_of, self.scats.first_id)
 
 
 class Engine:
@@ -157,13 +218,14 @@ class Engine:
             return np.empty(max(nbytes, 1), dtype=np.uint8)[:nbytes]
         buf = self._pinned.get(key)
         if buf is None or buf.nbytes < nbytes:
-            if pinned:
-                import torch
-                t = torch.empty(max(nbytes, 1), dtype=torch.uint8, pin_memory=True)
-                buf = t.numpy()
-                self._pinned[key + '_t'] = t
-            else:
-                buf = np.empty(max(nbytes, 1), dtype=np.uint8)
+            import torch
+            # page-locking is slow (~1-2 GB/s): over-allocate by 12 % so that batches of slightly different row
+            # counts reuse the same staging buffer
+            self._pinned.pop(key, None)
+            self._pinned.pop(key + '_t', None)
+            t = torch.empty(max(int(nbytes * 1.125) + 4096, 1), dtype=torch.uint8, pin_memory=True)
+            buf = t.numpy()
+            self._pinned[key + '_t'] = t
             self._pinned[key] = buf
         return buf[:nbytes]
 
@@ -245,23 +307,7 @@ class Engine:
             words = rawb.view(np.uint32).reshape(nsc, self.row_words)
         self.sync(stream)
         if words is not None:
-            scats['el'] = words[:, 0].astype(np.int64) + int(first_id)
-            scats['ev'] = (words[:, 1] & 0xffffff).astype(np.int32)
-            if self.word_of[0] >= 0:
-                scats['type'] = (words[:, 1] >> 24).astype(np.int8)
-            fl = words.view(np.float32)
-            names = {1: 'position', 2: 'pathl', 3: 'E', 4: 'E_loss', 5: 'pol_angle', 6: 'az_angle', 7: 'energy',
-                     8: 'direction'}
-            for b, nm in names.items():
-                w = self.word_of[b]
-                if w < 0:
-                    continue
-                if nm == 'position':
-                    scats['x'], scats['y'], scats['z'] = fl[:, w], fl[:, w + 1], fl[:, w + 2]
-                elif nm == 'direction':
-                    scats['direction'] = fl[:, w:w + 3]
-                else:
-                    scats[nm] = fl[:, w]
+            scats = ScatRows(words, self.word_of, first_id)
         return els, scats
 
     def run(self, count=None, first_id=None, max_scat_rows=None, pinned=False, stream=None, drain=True):

@@ -71,7 +71,8 @@ def _per_electron_dicts(eng, res, inputPar, thingsToSave):
     cont = 'DS' not in inputPar['mode']
     sc = res.sorted_scats()
     n = res.count
-    if sc:
+    have_sc = len(sc) > 0
+    if have_sc:
         bounds = np.searchsorted(sc['el'], np.arange(res.first_id, res.first_id + n + 1))
     double = bool(inputPar.get('reference_double_record', False))
     out = []
@@ -93,7 +94,7 @@ def _per_electron_dicts(eng, res, inputPar, thingsToSave):
                 els[c] = {'last_x': [float(r['last_x'])] * k, 'last_y': [float(r['last_y'])] * k,
                           'last_z': [float(r['last_z'])] * k}
         scd = {}
-        lo, hi = (bounds[i], bounds[i + 1]) if sc else (0, 0)
+        lo, hi = (bounds[i], bounds[i + 1]) if have_sc else (0, 0)
         for c in sc_cols:
             if cont and c in ('position', 'E'):
                 scd[c] = {'x': [], 'y': [], 'z': []} if c == 'position' else []
