@@ -1,0 +1,67 @@
+"""GPU: the doScatter-style command line end to end (input.file -> tables -> run -> store) and the drop-in
+workers with the reference's signatures."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cli_writes_reference_layout(tmp_path):
+    inp = tmp_path / 'input.file'
+    inp.write_text('\n'.join([
+        'num_el : 3000', 'E0 : 20000 # eV', 'Emin : 15000', 'material : Si', 's_tilt : 70', 'thickness : 3000000',
+        'elastic : Ruth_vanilla', 'mode : DS', 'Bethe_model : classical', 'diffMFP : no', 'gen_tables : yes',
+        'tol_E : 1e-2', 'tol_W : 1e-3', 'maxScatt: 1000', 'Wc : 10',
+        'electron_output : outcome, final_E, final_dir, last_pos', 'scatter_output : type, position, energy']))
+    out = str(tmp_path / 'run.parquet')
+    r = subprocess.run([sys.executable, '-m', 'mcdiscrete_b200', '-i', str(inp), '-o', out, '--format', 'parquet',
+                        '--batch', '1000'], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    from mcdiscrete_b200.store import read_store
+    back = read_store(out)
+    assert len(back['els']) == 3000
+    assert list(back['els'].columns) == ['outcome', 'final_E', 'dx', 'dy', 'dz', 'last_x', 'last_y', 'last_z']
+    assert list(back['scats'].columns) == ['type', 'energy', 'x', 'y', 'z']
+    assert set(back['els']['outcome']) <= {'abs', 'bks', 'trsm', 'long'}
+    assert set(back['scats']['type']) <= {'Ruth', 'Moller', 'Gryz1s', 'Gryz2s', 'Gryz2p', 'Quinn'}
+    first = back['scats'][(back['scats'][['x', 'y', 'z']] == 0).all(axis=1)]
+    assert len(first) == 3000                                   # every trajectory starts at the origin
+    st = json.load(open(out + '.stats.json'))
+    assert sum(st['histograms']['energy']['counts']) == int((back['els']['outcome'] == 'bks').sum())
+
+
+def test_workers_with_reference_signatures():
+    from mcdiscrete_b200 import material, genTables, multiTraj_DS, multiTraj_cont, zipDict
+    ip = dict(num_el=8, E0=20000., Emin=15000., material='Si', s_tilt=70., thickness=3e6, elastic='Ruth_vanilla',
+              mode='DS', Bethe_model='classical', diffMFP=False, gen_tables=True, tol_E=1e-2, tol_W=1e-3,
+              maxScatt=1000, Wc=10., electron_output=['outcome', 'final_E', 'final_dir', 'last_pos'],
+              scatter_output=['type', 'position', 'energy'])
+    what = {'el_output': ip['electron_output'], 'scat_output': ip['scatter_output']}
+    mat = material(ip['material'])
+    tables = genTables(ip)
+    res = multiTraj_DS(ip, 8, mat, tables, what)                 # multiScatter.py:66 signature
+    assert len(res) == 8 and set(res[0]) == {'els', 'scats'}
+    r0 = res[0]
+    assert list(r0['els']) == ['outcome', 'final_E', 'final_dir', 'last_pos']
+    assert set(r0['els']['final_dir']) == {'dx', 'dy', 'dz'} and set(r0['els']['last_pos']) == {'last_x', 'last_y', 'last_z'}
+    n = len(r0['scats']['type'])
+    assert n == len(r0['scats']['energy']) == len(r0['scats']['position']['x']) >= 1
+    assert r0['scats']['position']['x'][0] == 0.0 and r0['scats']['type'][0] in ('Ruth', 'Moller', 'Quinn', 'Gryz1s', 'Gryz2s', 'Gryz2p')
+    # the listener's merge (doScatter.py:108-110) works on the returned structure
+    merged = {}
+    for r in res:
+        merged = zipDict(merged, r['scats'])
+    assert list(merged) == ['type', 'energy', 'x', 'y', 'z']
+    again = multiTraj_DS(ip, 8, mat, tables, what)               # fresh electrons on every call
+    assert [r['els']['final_E'] for r in again] != [r['els']['final_E'] for r in res]
+    ipc = dict(ip, mode='cont', Emin=500., Bethe_model='JL', scatter_output=['type', 'pathl', 'E_loss', 'energy'])
+    whatc = {'el_output': ip['electron_output'], 'scat_output': ipc['scatter_output']}
+    resc = multiTraj_cont(ipc, 4, material('Si'), whatc, {})      # multiScatter.py:171 argument order
+    assert len(resc) == 4 and resc[0]['scats']['type'][0] == 'Ruth_vanilla'
+    assert len(resc[0]['scats']['pathl']) == len(resc[0]['scats']['energy'])

@@ -1,0 +1,87 @@
+"""CPU-only: the result store keeps the reference's keys / columns / order, and the CLI parses the reference's options."""
+import os
+
+import numpy as np
+import pytest
+
+from mcdiscrete_b200 import _lib
+from mcdiscrete_b200.engine import RunResult, ScatRows
+from mcdiscrete_b200.store import ResultStore, read_store, store_name, els_frame, scats_frame
+
+
+def _fake_result(n_el=5):
+    els = np.zeros(n_el, _lib.EL_ROW_DTYPE)
+    els['code'] = [0, 1, 1 | 0x100, 4, 0]
+    els['final_E'] = np.linspace(11000, 19000, n_el)
+    els['dx'], els['dy'], els['dz'] = 0.1, 0.2, -0.9
+    els['last_x'], els['last_y'], els['last_z'] = 1.0, 2.0, 3.0
+    # layout for scatter_output = type, position, energy: words [rel_id, ev|ch<<24, x, y, z, energy]
+    word_of = [1, 2, -1, -1, -1, -1, -1, 5, -1] + [-1] * 7
+    rows = []
+    for el, nev in enumerate([3, 1, 2, 2, 1]):
+        for ev in range(nev):
+            rows.append((el, ev | ((ev % 6) << 24), float(el), float(ev), 0.5, 20000. - 16.6 * ev))
+    w = np.zeros((len(rows), 6), np.uint32)
+    fl = w.view(np.float32)
+    rng = np.random.default_rng(0).permutation(len(rows))      # append order is not trajectory order
+    for k, r in enumerate(rows):
+        i = rng[k]
+        w[i, 0], w[i, 1] = r[0], r[1]
+        fl[i, 2], fl[i, 3], fl[i, 4], fl[i, 5] = r[2], r[3], r[4], r[5]
+    return RunResult(100, n_el, els, ScatRows(w, word_of, 100), {}, 0.0), rows
+
+
+IP = dict(num_el=5, E0=20000., Emin=10000., material='Si', s_tilt=70., thickness=3e6, elastic='Ruth_vanilla', mode='DS',
+          diffMFP=False, tol_E=1e-4, tol_W=1e-7, maxScatt=1000, Wc=10.,
+          electron_output=['outcome', 'final_E', 'final_dir', 'last_pos'], scatter_output=['type', 'position', 'energy'])
+NAMES = ['Ruth', 'Moller', 'Gryz1s', 'Gryz2s', 'Gryz2p', 'Quinn']
+
+
+def test_frames_follow_the_reference_column_contract():
+    res, rows = _fake_result()
+    e = els_frame(res, IP)
+    assert list(e.columns) == ['outcome', 'final_E', 'dx', 'dy', 'dz', 'last_x', 'last_y', 'last_z']
+    assert list(e['outcome']) == ['abs', 'bks', 'bks', 'long', 'abs']
+    assert e['final_E'].dtype == np.float64
+    e2 = els_frame(res, IP, double_record=True)                 # the reference's second 'abs' row
+    assert list(e2['outcome']) == ['abs', 'bks', 'bks', 'abs', 'long', 'abs']
+    s = scats_frame(res, IP, NAMES)
+    assert list(s.columns) == ['type', 'energy', 'x', 'y', 'z']  # zipDict order (fileTools.py:72-91)
+    assert len(s) == len(rows)
+    assert list(s['x']) == [float(r[2]) for r in rows]           # regrouped per electron, event order
+    assert list(s['y']) == [float(r[3]) for r in rows]
+    assert list(s['type'][:3]) == ['Ruth', 'Moller', 'Gryz1s']
+
+
+def test_store_roundtrip_parquet(tmp_path):
+    res, rows = _fake_result()
+    path = str(tmp_path / 'run.parquet')
+    with ResultStore(path, IP, fmt='parquet') as st:
+        st.append_result(res, NAMES)
+        st.append_result(res, NAMES)                             # appendable
+    back = read_store(path)
+    assert back['input']['material'] == 'Si' and back['input']['num_el'] == '5'
+    assert len(back['els']) == 10 and len(back['scats']) == 2 * len(rows)
+    assert list(back['els'].columns) == ['outcome', 'final_E', 'dx', 'dy', 'dz', 'last_x', 'last_y', 'last_z']
+    assert list(back['scats'].columns) == ['type', 'energy', 'x', 'y', 'z']
+
+
+def test_store_hdf5_when_pytables_is_available(tmp_path):
+    pytest.importorskip('tables')
+    res, rows = _fake_result()
+    path = str(tmp_path / 'run.h5')
+    with ResultStore(path, IP, fmt='hdf5') as st:
+        st.append_result(res, NAMES)
+    back = read_store(path)
+    assert len(back['els']) == 5 and list(back['scats'].columns) == ['type', 'energy', 'x', 'y', 'z']
+
+
+def test_store_name_and_cli_options():
+    from mcdiscrete_b200.doScatter import dealWithInput
+    name = store_name(IP)
+    assert name == ('../data/TRSM_diff:False_thick:3000000.0_mat:Si_mode:DS_elastic:Ruth_vanilla_tilt:70.0'
+                    '_Emin:10000.0_E0:20000.0_tolE:0.0001_tolW:1e-07.h5')
+    u, f, out, fmt, batch = dealWithInput(['-u', '-i', 'x.file', '--format', 'parquet', '--batch', '1000'])
+    assert (u, f, out, fmt, batch) == (True, 'x.file', None, 'parquet', 1000)
+    with pytest.raises(SystemExit):
+        dealWithInput(['-h'])
