@@ -109,29 +109,27 @@ traj_kernel(const __grid_constant__ DevParams P, const DevOut O, const unsigned 
     if (!__any_sync(MCD_FULL_MASK, alive)) break;
 
     // ---- one loop iteration of trajectory_DS / trajectory_cont_cl ---------------------------
-    bool has_row = false;
-    int outcome = -1;
+    // an alive lane either executes one event or, past maxScatt, retires as 'long' (singleScatter.py:19-23)
+    const bool has_row = alive && (ev < (uint32_t)P.maxScatt);
+    int outcome = (alive && !has_row) ? MCD_OUT_LONG : -1;
     EventRow row;
     OutcomeSnap sn;
     row.flags = 0;
-    EventMid mid;
-    mid.tab = -1;
-    mid.invE = 0.f; mid.W = 0.f; mid.om = 0.f;
-    float4 u = make_float4(0.5f, 0.5f, 0.5f, 0.5f);
-    if (alive) {
-      if (ev >= (uint32_t)P.maxScatt) {                          // singleScatter.py:19-23
-        outcome = MCD_OUT_LONG;
-        snap(sn, e);
+    row.slot = 0;
+    if (has_row) {
+      const float4 u = event_uniforms(P, first_id + rel_id, ev);
+      if (MODE == MCD_MODE_DS) {
+        EventMid mid;
+        ds_phase_a<S>(P, e, u, row, sn, mid);
+        ds_phase_b(P, e, u, row, sn, mid);
       } else {
-        u = event_uniforms(P, first_id + rel_id, ev);
-        if (MODE == MCD_MODE_DS) ds_phase_a<S>(P, e, u, row, sn, mid);
-        else cont_event(P, e, u, row, sn);
-        has_row = true;
-        ++my_events;
+        cont_event(P, e, u, row, sn);
       }
+      outcome = row.outcome;
+      ++my_events;
+    } else if (outcome == MCD_OUT_LONG) {
+      snap(sn, e);
     }
-    if (MODE == MCD_MODE_DS && has_row) ds_phase_b(P, e, u, row, sn, mid);
-    if (has_row) outcome = row.outcome;
 
     // ---- scats append: warp-local slots in the warp's chunk; a new chunk when it is full --------
     if (want_scats) {
