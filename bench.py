@@ -52,7 +52,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '20'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -102,7 +102,7 @@ def run_reference(args, rank):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_el = 20000
+    n_el = 400000                      # ~2.5 s of work per step on 16 threads
     tables = None
     vals, evs = [], []
     for s in range(args.warmup + args.steps):
@@ -136,7 +136,7 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours')
     ap.add_argument('--num-el', type=int, default=NUM_EL)
@@ -306,10 +306,10 @@ def main():
         }
         if not args.no_cpu and world == 1:
             cores = os.cpu_count() or 1
-            el_s, ev_s, dtc, _ = cpu_sample(40000, cores)
+            el_s, ev_s, dtc, _ = cpu_sample(2000000, cores)
             out['cpu_baseline'] = {'value': el_s, 'unit': 'electrons/s', 'cores': cores, 'kind': 'port',
                                    'events_per_s': ev_s,
-                                   'sample': '40000 electrons of workload C2 (%.1f s), oracle C restatement of the '
+                                   'sample': '2e6 electrons of workload C2 (%.1f s), oracle C restatement of the '
                                              'reference loop, %d threads; tables at tol_E 1e-3 / tol_W 1e-5' % (dtc, cores)}
         print(json.dumps(out))
     if world > 1:
