@@ -154,3 +154,74 @@ def test_reference_stochastic_checks_on_scats():
     c2 = sc['pol_angle'][mol0].astype(np.float64)
     assert np.allclose(c2, 0.5 * (np.sqrt(1 - W / 20000.) + 1), rtol=2e-6)      # binaryCollModel
     eng.close()
+
+
+def test_thin_film_transmission_and_low_Emin():
+    """'trsm' (electron.py:73-81) on a 1500 A film, and a run down to Emin = 500 eV where the channel order
+    changes with energy (the per-event order check is active) -- both against independent oracle samples."""
+    ip = dict(E0=20000., Emin=500., material='Si', s_tilt=0., thickness=1500., mode='DS', maxScatt=10000, Wc=10.,
+              tol_E=1e-3, tol_W=1e-4, electron_output=['outcome', 'final_E', 'final_dir', 'last_pos'],
+              scatter_output=[], seed=11)
+    tabs = o.gen_tables(ip, strict=False)
+    n_gpu, n_ref = 200000, 40000
+    eng = _engine(ip, tabs)
+    res = eng.run(count=n_gpu, first_id=0)
+    ref = oc.run(ip, 0, n_ref, 555, tabs, nthreads=os.cpu_count() or 1)
+    out = res.outcome
+    for code in (0, 1, 2):                                       # abs, bks, trsm fractions within 3 sigma
+        pg, pr = (out == code).mean(), (ref['outcome'] == code).mean()
+        sig = math.sqrt(pg * (1 - pg) / n_gpu + pr * (1 - pr) / n_ref) + 1e-12
+        assert abs(pg - pr) < 3 * sig, (code, pg, pr)
+    assert (out == 2).mean() > 0.5                               # most 20 keV electrons cross 150 nm of Si
+    tg, tr = out == 2, ref['outcome'] == 2
+    rng = np.random.default_rng(0)
+    jit = lambda x: np.asarray(x, np.float64) + rng.uniform(-0.05, 0.05, len(x))
+    assert stats.ks_2samp(jit(res.els['final_E'][tg]), jit(ref['final_E'][tr])).pvalue > P_MIN
+    assert stats.ks_2samp(res.els['dz'][tg].astype(np.float64), ref['final_dir'][tr, 2]).pvalue > P_MIN
+    assert (res.els['dz'][tg] > 0).all() and (res.els['last_z'][tg] < 1500.).all()
+    eng.close()
+    # thick sample, Emin = 500 eV: long trajectories, order changes below ~2.6 keV for some materials
+    ip2 = dict(ip, thickness=3e6, s_tilt=70., material='Cu')
+    tabs2 = o.gen_tables(ip2, strict=False)
+    eng = _engine(ip2, tabs2)
+    res = eng.run(count=100000, first_id=0)
+    ref = oc.run(ip2, 0, 20000, 556, tabs2, nthreads=os.cpu_count() or 1)
+    _compare(res, ref, 100000, 20000, lambda: oc.run(ip2, 0, 20000, 557, tabs2, nthreads=os.cpu_count() or 1))
+    same = oc.run(ip2, 0, 5000, 11, tabs2, nthreads=os.cpu_count() or 1)
+    assert (res.outcome[:5000] == same['outcome']).mean() > 0.995
+    assert res.counters['select_exact'] > 0
+    eng.close()
+
+
+def test_gryz_per_shell_mode():
+    """gryz_table='per_shell' (the non-quirk variant): each Gryzinski shell samples its own table.
+    Checked against the oracle run with gryz_per_shell=True on the same Philox streams."""
+    from mcdiscrete_b200.engine import Engine
+    ip = dict(E0=20000., Emin=15000., material='Si', s_tilt=70., thickness=3e6, mode='DS', maxScatt=1000, Wc=10.,
+              tol_E=1e-2, tol_W=1e-3, electron_output=['outcome', 'final_E'], scatter_output=['type', 'E_loss'], seed=3)
+    tabs = o.gen_tables(ip, gryz='all')
+    eng = Engine(ip, device=0, gryz_table='per_shell')
+    eng.table_upload(0, tabs['Moller'].Es, tabs['Moller'].Ws, tabs['Moller'].table)
+    for k, T in enumerate(tabs['Gryz']):
+        eng.table_upload(1 + k, T.Es, T.Ws, T.table)
+    eng.tables = tabs
+    n = 3000
+    res = eng.run(count=n, first_id=0)
+    els = o.run_electrons(ip, 0, 300, 3, tabs, gryz_per_shell=True)
+    sc = res.sorted_scats()
+    nev = np.bincount((sc['el']).astype(np.int64), minlength=n)
+    off = np.concatenate([[0], np.cumsum(nev)])
+    agree = 0
+    for i, e in enumerate(els):
+        if nev[i] == len(e.scats) and res.outcome[i] == o.OUTCOMES.index(e.els[0][0]):
+            agree += 1
+            W = np.array([r['E_loss'] for r in e.scats])
+            assert np.allclose(sc['E_loss'][off[i]:off[i + 1]], W, rtol=2e-6, atol=1e-6)
+    assert agree >= 290
+    # inner-shell events lose at least their own binding energy (with the quirk they could lose only 100 eV)
+    mat = o.Material('Si')
+    for ch, Eb in ((2, 1189.), (3, 149.), (4, 100.)):
+        sel = res.scats['type'] == ch
+        if sel.any():
+            assert res.scats['E_loss'][sel].min() >= Eb * (1 - 1e-6)
+    eng.close()
