@@ -172,9 +172,14 @@ def main():
     torch.cuda.synchronize()
     t_tables = time.time() - t0
     table_bytes = sum(4 * len(T.Es) * (len(T.Ws) - 1) for T in [tabs['Moller']] + tabs['Gryz'])
-    eng.set_capacity(n_el, 0)
+    # two contexts sharing the tables, one CUDA stream each: consecutive steps are pipelined, so the blocks of
+    # step k+1 fill the SMs that the tail of step k leaves idle (1e6 electrons are only 6.6 per resident lane)
+    engs = [eng, eng.clone()]
+    tstreams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for e in engs:
+        e.set_capacity(n_el, 0)
     stream = torch.cuda.current_stream().cuda_stream
-    stats = eng.stats_tensor()
+    stats = [e.stats_tensor() for e in engs]
 
     # measured compute roofs of this GPU (FMA and MUFU chains)
     import ctypes as C
@@ -194,35 +199,40 @@ def main():
         step_id[0] += 1
         return fid
 
-    def device_step():
-        eng.reset_stats(stream)
-        eng.launch(first_id(), n_el, stream)
-        if world > 1:
-            allreduce_stats(stats)
+    def device_step(k):
+        e, ts = engs[k % 2], tstreams[k % 2]
+        with torch.cuda.stream(ts):
+            e.reset_stats(ts.cuda_stream)
+            e.launch(first_id(), n_el, ts.cuda_stream)
+            if world > 1:
+                allreduce_stats(stats[k % 2])
 
     # ---- device-timed throughput ------------------------------------------------------------------------
-    for _ in range(args.warmup):
-        device_step()
+    for k in range(args.warmup):
+        device_step(k)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.3)
     kernel_ms = []
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
     tw0 = time.time()
-    ev0.record()
-    for _ in range(args.steps):
-        device_step()
-    ev1.record()
+    ev0.record(tstreams[0])
+    tstreams[1].wait_event(ev0)                      # both streams start after the same timestamp
+    for k in range(args.steps):
+        device_step(k)
+    ev1[0].record(tstreams[0])
+    ev1[1].record(tstreams[1])
     barrier()
     tw1 = time.time()
-    ms = ev0.elapsed_time(ev1)
+    ms = max(ev0.elapsed_time(ev1[0]), ev0.elapsed_time(ev1[1]))
     clocks = sampler.stop(tw0, tw1)
     tmax = torch.tensor([ms], device='cuda')
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms = float(tmax.item())
-    cnt = eng.counters()                      # of the last step (summed over ranks when world > 1)
+    cnt = engs[(args.steps - 1) % 2].counters()   # of the last step (summed over ranks when world > 1)
     events_per_step = cnt['events']           # whole job
     electrons_per_step = cnt['electrons_done']
     assert electrons_per_step == n_el * world, (electrons_per_step, n_el, world)
@@ -266,15 +276,17 @@ def main():
     # ---- end to end through the public API with pinned host outputs ------------------------------------------
     h2d = C.sizeof(_lib.Params) + 1024      # launch parameter block: there are no per-step input arrays
     d2h = n_el * 32 + 8 * (_lib.HIST_TOTAL + C.sizeof(_lib.Counters) // 8)
-    for _ in range(2):
-        eng.run(count=n_el, first_id=first_id(), pinned=True, stream=stream)
+    def e2e_pass(nsteps):
+        last = None
+        hook = (lambda e, ts: allreduce_stats(e.stats_tensor())) if world > 1 else None
+        for r in eng.run_batches(nsteps * n_el, n_el, first_id=first_id() + 10 ** 12, on_launched=hook):
+            last = r                                  # rows are in pinned host memory here
+            _ = int(r.els['code'][0]) + r.counters['events']
+        return last
+    e2e_pass(2)
     barrier()
     t0 = time.time()
-    for _ in range(args.steps):
-        r = eng.run(count=n_el, first_id=first_id(), pinned=True, stream=stream)
-        h = eng.histograms()
-        if world > 1:
-            allreduce_stats(stats)
+    r = e2e_pass(args.steps)
     barrier()
     dt = time.time() - t0
     tdt = torch.tensor([dt], device='cuda')
@@ -282,6 +294,7 @@ def main():
         dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
     e2e = n_el * world * args.steps / float(tdt.item())
     eta = float((r.outcome == 1).mean())
+    cnt_e2e = r.counters
 
     if rank == 0:
         out = {
@@ -293,7 +306,8 @@ def main():
                        's_tilt_deg': 70, 'tol_E': 1e-4, 'tol_W': 1e-7, 'maxScatt': 1000, 'num_el_per_gpu': n_el,
                        'outputs': 'one els row per electron + fused backscatter histograms + counters',
                        'cache': 'inputs larger than L2 (inverse-CDF tables %.2f GB resident in HBM)' % (table_bytes / 1e9),
-                       'parallelism': 'electron ids partitioned across %d GPU(s); int64 histogram all-reduce' % world},
+                       'parallelism': 'electron ids partitioned across %d GPU(s); int64 histogram all-reduce' % world,
+                       'pipelining': 'steps alternate between two contexts / two streams (shared tables)'},
             'e2e': {'value': e2e, 'unit': 'electrons/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
             'gpu_launches': args.steps,
             'clocks': clocks,

@@ -155,6 +155,11 @@ int mcd_device_info(int device, char* name, int name_len, int* sm_count, int* cc
 
 int mcd_create(const mcd_params* p, const mcd_material* m, int device, mcd_ctx** out);
 int mcd_destroy(mcd_ctx* ctx);
+/* A second context on the same device that SHARES the parent's tables (read-only) but owns its own output
+ * buffers, ticket and statistics block: two contexts on two streams let the host drain batch k while batch k+1
+ * runs, and let the next kernel fill the SMs that the previous kernel's tail leaves idle.  Destroy clones
+ * before their parent; tables built/uploaded on the parent after cloning are not seen by the clone. */
+int mcd_clone(const mcd_ctx* parent, mcd_ctx** out);
 
 /* ---- tables -------------------------------------------------------------------------- */
 /* Build table `slot` on the device from host axes (float32, as found by the host axis search that

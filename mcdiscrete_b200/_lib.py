@@ -69,6 +69,7 @@ SYMBOLS = {
                                   C.POINTER(C.c_int), C.POINTER(_U64)]),
     'mcd_create': (C.c_int, [C.POINTER(Params), C.POINTER(Material), C.c_int, C.POINTER(_P)]),
     'mcd_destroy': (C.c_int, [_P]),
+    'mcd_clone': (C.c_int, [_P, C.POINTER(_P)]),
     'mcd_table_build': (C.c_int, [_P, C.c_int, _F, C.c_uint32, _F, C.c_uint32, C.c_double, C.c_double, _P]),
     'mcd_table_upload': (C.c_int, [_P, C.c_int, _F, C.c_uint32, _F, C.c_uint32, _F]),
     'mcd_table_shape': (C.c_int, [_P, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),

@@ -37,6 +37,7 @@ struct mcd_ctx {
   mcd_material mat;
   DevParams P;
   HostTable tab[MCD_MAX_TABLES];
+  bool owns_tables = true;
   // outputs
   mcd_el_row* els = nullptr;
   uint64_t max_el = 0;
@@ -233,6 +234,7 @@ int alloc_table(mcd_ctx* c, int slot, const float* Es, uint32_t nE, const float*
                 double es_start_hint) {
   if (slot < 0 || slot >= MCD_MAX_TABLES) return fail(c, MCD_ERR_INVALID, "table slot %d out of range", slot);
   if (nE < 2 || nW < 3 || !Es || !Ws) return fail(c, MCD_ERR_INVALID, "table axes too small (nE=%u nW=%u)", nE, nW);
+  if (!c->owns_tables) return fail(c, MCD_ERR_STATE, "tables of a cloned context belong to its parent");
   HostTable& h = c->tab[slot];
   free_table(h);
   CU(c, cudaMalloc(&h.cdf, (size_t)nE * (nW - 1) * sizeof(float)));
@@ -373,10 +375,39 @@ int mcd_create(const mcd_params* p, const mcd_material* m, int device, mcd_ctx**
   return MCD_OK;
 }
 
+int mcd_clone(const mcd_ctx* parent, mcd_ctx** out) {
+  if (!parent || !out) return fail(nullptr, MCD_ERR_INVALID, "null argument");
+  *out = nullptr;
+  cudaError_t e = cudaSetDevice(parent->device);
+  if (e != cudaSuccess) return fail(nullptr, MCD_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  mcd_ctx* c = new (std::nothrow) mcd_ctx();
+  if (!c) return fail(nullptr, MCD_ERR_NOMEM, "out of host memory");
+  c->device = parent->device;
+  c->sm_count = parent->sm_count;
+  c->par = parent->par;
+  c->mat = parent->mat;
+  c->P = parent->P;                      // includes the table descriptors (device pointers)
+  for (int s = 0; s < MCD_MAX_TABLES; ++s) c->tab[s] = parent->tab[s];
+  c->owns_tables = false;
+  c->li = parent->li;
+  c->n_blocks = parent->n_blocks;
+  if ((e = cudaMalloc(&c->ticket, sizeof(unsigned long long))) != cudaSuccess ||
+      (e = cudaMalloc(&c->stats, kStatsWords * 8)) != cudaSuccess ||
+      (e = cudaMalloc(&c->chunk_next, sizeof(unsigned int))) != cudaSuccess ||
+      (e = cudaMemset(c->stats, 0, kStatsWords * 8)) != cudaSuccess ||
+      (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess) {
+    std::string msg = cudaGetErrorString(e);
+    mcd_destroy(c);
+    return fail(nullptr, MCD_ERR_CUDA, "clone allocation: %s", msg.c_str());
+  }
+  *out = c;
+  return MCD_OK;
+}
+
 int mcd_destroy(mcd_ctx* c) {
   if (!c) return MCD_OK;
   cudaSetDevice(c->device);
-  for (auto& t : c->tab) free_table(t);
+  if (c->owns_tables) for (auto& t : c->tab) free_table(t);
   cudaFree(c->els); cudaFree(c->scats); cudaFree(c->chunk_next); cudaFree(c->chunk_count); cudaFree(c->ticket);
   cudaFree(c->stats);
   if (c->ev0) cudaEventDestroy(c->ev0);

@@ -173,7 +173,23 @@ class Engine:
         self._pinned = {}
 
     # ---- lifetime -----------------------------------------------------------------------------
+    def clone(self):
+        """A second context sharing this engine's tables (mcd_clone) with its own outputs and statistics."""
+        import copy
+        other = copy.copy(self)
+        other.ctx = C.c_void_p()
+        check(self.lib.mcd_clone(self.ctx, C.byref(other.ctx)), self.ctx)
+        other.cap_el = other.cap_sc = 0
+        other._pinned = {}
+        other._parent = self                      # keep the owner of the tables alive
+        other._clones = []
+        self._clones = getattr(self, '_clones', []) + [other]
+        return other
+
     def close(self):
+        for c in getattr(self, '_clones', []):    # clones first: they borrow this context's tables
+            c.close()
+        self._clones = []
         if getattr(self, 'ctx', None) is not None and self.ctx.value:
             self.lib.mcd_destroy(self.ctx)
             self.ctx = C.c_void_p()
@@ -340,6 +356,53 @@ class Engine:
         self.next_id = max(self.next_id, first_id + count)
         els, scats = self.drain(first_id, count, pinned=pinned, stream=stream) if drain else (None, {})
         return RunResult(first_id, count, els, scats, cnt, self.kernel_ms())
+
+    def run_batches(self, total, batch, first_id=0, max_scat_rows=None, on_launched=None):
+        """Simulate `total` electrons in batches of `batch`, PIPELINED over two contexts / two CUDA streams:
+        while the host drains batch k (D2H into pinned buffers) batch k+1 already runs, and its blocks fill the
+        SMs that the tail of batch k leaves idle.  Yields one RunResult per batch, in order.  Rows of a yielded
+        result live in reused pinned buffers: consume them before advancing the generator twice.
+        `on_launched(engine, torch_stream)` is called right after each launch (e.g. to enqueue the NCCL
+        all-reduce of engine.stats_tensor() on that stream)."""
+        import torch
+        if self.params.mode == _lib.MODE_DS and self.tables is None:
+            from .probTables import genTables
+            genTables(self.inputPar, engine=self)
+        engs = [self, self.clone()]
+        streams = [torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device)]
+        if max_scat_rows is None:
+            max_scat_rows = (batch * min(int(self.inputPar['maxScatt']), 512) + 65536) if self.row_words else 0
+        pending = None
+
+        def finish(p):
+            e, st, first, cnt = p
+            e.sync(st)
+            cnts = e.counters()
+            if cnts['scat_rows_dropped']:
+                raise _lib.MCDError(-5, '%d scats rows did not fit: raise max_scat_rows or lower batch' % cnts['scat_rows_dropped'])
+            els, scats = e.drain(first, cnt, pinned=True, stream=st)
+            return RunResult(first, cnt, els, scats, cnts, e.kernel_ms())
+        k = 0
+        try:
+            for first in range(first_id, first_id + total, batch):
+                cnt = min(batch, first_id + total - first)
+                e, st = engs[k % 2], streams[k % 2].cuda_stream
+                e.set_capacity(max(batch, e.cap_el), max(max_scat_rows, e.cap_sc))
+                e.reset_stats(st)
+                e.launch(first, cnt, st)
+                if on_launched is not None:
+                    with torch.cuda.stream(streams[k % 2]):
+                        on_launched(e, streams[k % 2])
+                if pending is not None:
+                    yield finish(pending)
+                pending = (e, st, first, cnt)
+                k += 1
+            if pending is not None:
+                yield finish(pending)
+            self.next_id = max(self.next_id, first_id + total)
+        finally:
+            engs[1].close()
+            self._clones = [c for c in getattr(self, '_clones', []) if c is not engs[1]]
 
     # ---- unit hooks (parity tests) --------------------------------------------------------------
     def test_sigmas(self, E):

@@ -461,3 +461,23 @@ def test_run_properties_full_size():
     eta = (out == 1).mean()
     assert 0.3 < eta < 0.7
     eng.close()
+
+
+def test_pipelined_batches_equal_single_run():
+    """Engine.run_batches (two contexts sharing the tables, two streams) yields exactly the rows of one run."""
+    ip = dict(scatter_output=['type', 'energy'], Emin=15000.)
+    eng = make_engine(**ip)
+    upload_golden(eng, golden_tables('Si_15k_small'))
+    N = 60000
+    whole = eng.run(count=N, first_id=1000)
+    els_whole = whole.els.copy()
+    ev_whole = whole.counters['events']
+    parts, ev, nrows = [], 0, 0
+    for r in eng.run_batches(N, 17000, first_id=1000):
+        parts.append(r.els.copy())
+        ev += r.counters['events']
+        nrows += len(r.scats)
+        assert r.counters['electrons_done'] == r.count
+    assert np.array_equal(np.concatenate(parts), els_whole)
+    assert ev == ev_whole == nrows
+    eng.close()
