@@ -190,6 +190,15 @@ int mcd_row_counts(mcd_ctx* ctx, uint64_t* n_els, uint64_t* n_scats);
 int mcd_drain_els(mcd_ctx* ctx, mcd_el_row* host, uint64_t offset, uint64_t n, void* stream);
 /* Copy scats rows [offset, offset+n) (append order; use words 0/1 to regroup) to host. */
 int mcd_drain_scats(mcd_ctx* ctx, uint32_t* host_words, uint64_t offset, uint64_t n, void* stream);
+/* Regroup the stored scats rows of the last run ON THE DEVICE into the reference's row order (electron after
+ * electron in id order, events in order; multiScatter.py:107-112): a scan of the per-electron event counts gives
+ * row offsets, one pass scatters the appended rows to offsets[id] + event.  Needs a second row buffer of the same
+ * size and no dropped rows.  Afterwards mcd_drain_scats_ordered copies rows [offset, offset+n) of the ordered
+ * array and mcd_scat_offsets copies offsets[first .. first+n] (n+1 values; electron i owns rows
+ * offsets[i] .. offsets[i+1]-1). */
+int mcd_order_scats(mcd_ctx* ctx, void* stream);
+int mcd_drain_scats_ordered(mcd_ctx* ctx, uint32_t* host_words, uint64_t offset, uint64_t n, void* stream);
+int mcd_scat_offsets(mcd_ctx* ctx, uint64_t* host, uint64_t first, uint64_t n, void* stream);
 int mcd_counters_get(mcd_ctx* ctx, mcd_counters* out);
 int mcd_hist_get(mcd_ctx* ctx, int64_t* host /* MCD_HIST_TOTAL */);
 /* Device address of the int64 histogram||counter block, for an in-place NCCL all-reduce by the caller

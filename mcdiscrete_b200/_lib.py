@@ -82,6 +82,9 @@ SYMBOLS = {
     'mcd_row_counts': (C.c_int, [_P, C.POINTER(_U64), C.POINTER(_U64)]),
     'mcd_drain_els': (C.c_int, [_P, _P, _U64, _U64, _P]),
     'mcd_drain_scats': (C.c_int, [_P, _P, _U64, _U64, _P]),
+    'mcd_order_scats': (C.c_int, [_P, _P]),
+    'mcd_drain_scats_ordered': (C.c_int, [_P, _P, _U64, _U64, _P]),
+    'mcd_scat_offsets': (C.c_int, [_P, C.POINTER(_U64), _U64, _U64, _P]),
     'mcd_counters_get': (C.c_int, [_P, C.POINTER(Counters)]),
     'mcd_hist_get': (C.c_int, [_P, C.POINTER(C.c_int64)]),
     'mcd_stats_device_ptr': (C.c_int, [_P, C.POINTER(_P), C.POINTER(_U64)]),

@@ -45,6 +45,13 @@ struct mcd_ctx {
   uint32_t n_chunks = 0;                      // chunk pool size (MCD_CHUNK_ROWS rows each)
   unsigned int* chunk_next = nullptr;
   unsigned int* chunk_count = nullptr;
+  unsigned int* nev = nullptr;                // events per electron of the last run
+  uint32_t* sorted = nullptr;                 // rows regrouped in trajectory order (mcd_order_scats)
+  uint64_t sorted_cap_rows = 0;
+  unsigned long long* offsets = nullptr;      // max_el + 1
+  unsigned long long* tile_tmp = nullptr;
+  unsigned long long* total_dev = nullptr;
+  bool ordered = false;
   unsigned long long* ticket = nullptr;
   unsigned long long* stats = nullptr;
   int n_blocks = 0;
@@ -409,6 +416,7 @@ int mcd_destroy(mcd_ctx* c) {
   cudaSetDevice(c->device);
   if (c->owns_tables) for (auto& t : c->tab) free_table(t);
   cudaFree(c->els); cudaFree(c->scats); cudaFree(c->chunk_next); cudaFree(c->chunk_count); cudaFree(c->ticket);
+  cudaFree(c->nev); cudaFree(c->sorted); cudaFree(c->offsets); cudaFree(c->tile_tmp); cudaFree(c->total_dev);
   cudaFree(c->stats);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -485,6 +493,11 @@ int mcd_set_capacity(mcd_ctx* c, uint64_t max_electrons, uint64_t max_scat_rows)
   cudaFree(c->els); c->els = nullptr;
   cudaFree(c->scats); c->scats = nullptr;
   cudaFree(c->chunk_count); c->chunk_count = nullptr;
+  cudaFree(c->nev); c->nev = nullptr;
+  cudaFree(c->sorted); c->sorted = nullptr; c->sorted_cap_rows = 0;
+  cudaFree(c->offsets); c->offsets = nullptr;
+  cudaFree(c->tile_tmp); c->tile_tmp = nullptr;
+  cudaFree(c->total_dev); c->total_dev = nullptr;
   c->max_el = 0; c->n_chunks = 0;
   CU(c, cudaMalloc(&c->els, max_electrons * sizeof(mcd_el_row)));
   c->max_el = max_electrons;
@@ -495,6 +508,7 @@ int mcd_set_capacity(mcd_ctx* c, uint64_t max_electrons, uint64_t max_scat_rows)
     if (nch >> 31) return fail(c, MCD_ERR_INVALID, "scats pool too large");
     CU(c, cudaMalloc(&c->scats, nch * MCD_CHUNK_ROWS * (uint64_t)c->P.scat_row_words * 4));
     CU(c, cudaMalloc(&c->chunk_count, nch * sizeof(unsigned int)));
+    CU(c, cudaMalloc(&c->nev, max_electrons * sizeof(unsigned int)));
     c->n_chunks = (uint32_t)nch;
   }
   return MCD_OK;
@@ -536,6 +550,7 @@ int mcd_run(mcd_ctx* c, uint64_t first_id, uint64_t count, void* stream) {
   O.n_chunks = c->n_chunks;
   O.chunk_next = c->chunk_next;
   O.chunk_count = c->chunk_count;
+  O.nev = c->nev;
   O.ticket = c->ticket;
   O.stats = c->stats;
   CU(c, cudaEventRecord(c->ev0, s));
@@ -543,6 +558,7 @@ int mcd_run(mcd_ctx* c, uint64_t first_id, uint64_t count, void* stream) {
   CU(c, cudaEventRecord(c->ev1, s));
   c->last_count = count;
   c->seg_cached = false;
+  c->ordered = false;
   c->timed = true;
   return MCD_OK;
 }
@@ -621,6 +637,63 @@ int mcd_drain_scats(mcd_ctx* c, uint32_t* host, uint64_t offset, uint64_t n, voi
     CU(c, cudaMemcpyAsync(host + done * rw, src, k * rw * 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     done += k;
   }
+  return MCD_OK;
+}
+
+int mcd_order_scats(mcd_ctx* c, void* stream) {
+  int rc = need_ctx(c);
+  if (rc) return rc;
+  if (!c->scats || !c->nev || !c->last_count) return fail(c, MCD_ERR_STATE, "no scats rows to order");
+  cudaStream_t s = (cudaStream_t)stream;
+  CU(c, cudaStreamSynchronize(s));
+  rc = cache_segments(c);
+  if (rc) return rc;
+  mcd_counters cn;
+  CU(c, cudaMemcpy(&cn, c->stats + MCD_HIST_TOTAL, sizeof cn, cudaMemcpyDeviceToHost));
+  if (cn.scat_rows_dropped) return fail(c, MCD_ERR_OVERFLOW, "rows were dropped: cannot regroup an incomplete run");
+  if (!c->offsets) {
+    CU(c, cudaMalloc(&c->offsets, (c->max_el + 1) * sizeof(unsigned long long)));
+    CU(c, cudaMalloc(&c->tile_tmp, mcd_order_tiles(c->max_el) * sizeof(unsigned long long)));
+    CU(c, cudaMalloc(&c->total_dev, sizeof(unsigned long long)));
+  }
+  if (c->sorted_cap_rows < c->rows_total) {
+    cudaFree(c->sorted); c->sorted = nullptr; c->sorted_cap_rows = 0;
+    const uint64_t cap = c->rows_total + c->rows_total / 8 + 1024;
+    CU(c, cudaMalloc(&c->sorted, cap * (uint64_t)c->P.scat_row_words * 4));
+    c->sorted_cap_rows = cap;
+  }
+  unsigned int used = 0;
+  CU(c, cudaMemcpy(&used, c->chunk_next, sizeof used, cudaMemcpyDeviceToHost));
+  if (used > c->n_chunks) used = c->n_chunks;
+  CU(c, mcd_launch_order_scats(c->nev, c->last_count, c->tile_tmp, c->offsets, c->total_dev, c->scats, c->chunk_count,
+                               used, c->P.scat_row_words, c->sorted, c->sm_count, s));
+  unsigned long long total = 0;
+  CU(c, cudaMemcpyAsync(&total, c->total_dev, sizeof total, cudaMemcpyDeviceToHost, s));
+  CU(c, cudaStreamSynchronize(s));
+  if (total != c->rows_total)
+    return fail(c, MCD_ERR_STATE, "event counts (%llu) and stored rows (%llu) disagree", total,
+                (unsigned long long)c->rows_total);
+  c->ordered = true;
+  return MCD_OK;
+}
+
+int mcd_drain_scats_ordered(mcd_ctx* c, uint32_t* host, uint64_t offset, uint64_t n, void* stream) {
+  int rc = need_ctx(c);
+  if (rc) return rc;
+  if (!c->ordered) return fail(c, MCD_ERR_STATE, "mcd_order_scats has not been called for the last run");
+  if (!host || offset + n > c->rows_total) return fail(c, MCD_ERR_INVALID, "scats range outside the stored rows");
+  const uint64_t rw = (uint64_t)c->P.scat_row_words;
+  if (n) CU(c, cudaMemcpyAsync(host, c->sorted + offset * rw, n * rw * 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return MCD_OK;
+}
+
+int mcd_scat_offsets(mcd_ctx* c, uint64_t* host, uint64_t first, uint64_t n, void* stream) {
+  int rc = need_ctx(c);
+  if (rc) return rc;
+  if (!c->ordered) return fail(c, MCD_ERR_STATE, "mcd_order_scats has not been called for the last run");
+  if (!host || first + n > c->last_count) return fail(c, MCD_ERR_INVALID, "offset range outside the last run");
+  CU(c, cudaMemcpyAsync(host, c->offsets + first, (n + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                        (cudaStream_t)stream));
   return MCD_OK;
 }
 

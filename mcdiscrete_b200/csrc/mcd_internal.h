@@ -27,6 +27,12 @@ cudaError_t mcd_launch_traj(const DevParams& P, const DevOut& O, unsigned long l
                             unsigned long long count, int sm_count, cudaStream_t stream, TrajLaunchInfo* info);
 cudaError_t mcd_traj_max_blocks(const DevParams& P, int sm_count, TrajLaunchInfo* info);
 
+cudaError_t mcd_launch_order_scats(const unsigned int* nev, unsigned long long count, unsigned long long* tile_tmp,
+                                   unsigned long long* offsets, unsigned long long* total_dev, const uint32_t* pool,
+                                   const unsigned int* chunk_count, unsigned int nchunks, int row_words,
+                                   uint32_t* sorted, int sm_count, cudaStream_t stream);
+unsigned long long mcd_order_tiles(unsigned long long count);
+
 // mcd_tables.cu
 cudaError_t mcd_launch_table_build(const TableBuildArgs& a, int blocks, cudaStream_t stream);
 cudaError_t mcd_launch_table_nvalid(const float* cdf, int nE, int nW, int* nvalid, cudaStream_t stream);

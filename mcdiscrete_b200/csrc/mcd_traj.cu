@@ -175,6 +175,7 @@ traj_kernel(const __grid_constant__ DevParams P, const DevOut O, const unsigned 
     // ---- retire: saveOutcomes row (electron.py:105-113), histograms, counters -------------------
     if (outcome >= 0) {
       const bool dbl = (row.flags & MCD_EVF_DOUBLE) != 0;
+      if (want_scats) O.nev[rel_id] = ev;
       float4* dst = reinterpret_cast<float4*>(O.els + rel_id);
       dst[0] = make_float4(__uint_as_float((uint32_t)outcome | (dbl ? 0x100u : 0u)), sn.E, sn.dx, sn.dy);
       dst[1] = make_float4(sn.dz, sn.x, sn.y, sn.z);
@@ -248,6 +249,126 @@ TrajKernel pick_kernel(const DevParams& P) {
 }
 
 }  // namespace
+
+// ---- regroup the appended scats rows into trajectory order (the reference's row order: electrons in id order,
+// events in order; multiScatter.py:107-112 appends one whole trajectory after the other) -------------------------
+namespace {
+
+constexpr int kScanT = 256;
+constexpr int kScanItems = 8;
+
+// offsets[i] = sum_{j<i} nev[j] (exclusive, 64 bit).  Three small kernels: per-tile sums, scan of the tile sums
+// by one block, per-tile exclusive scan plus tile offset.
+__global__ void scan_tile_sums(const unsigned int* __restrict__ nev, unsigned long long n,
+                               unsigned long long* __restrict__ tile_sum) {
+  __shared__ unsigned long long s_w[kScanT / 32];
+  const unsigned long long base = (unsigned long long)blockIdx.x * kScanT * kScanItems;
+  unsigned long long v = 0;
+  for (int k = 0; k < kScanItems; ++k) {
+    const unsigned long long i = base + (unsigned long long)k * kScanT + threadIdx.x;
+    if (i < n) v += nev[i];
+  }
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(MCD_FULL_MASK, v, d);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int w = 0; w < kScanT / 32; ++w) t += s_w[w];
+    tile_sum[blockIdx.x] = t;
+  }
+}
+
+__global__ void scan_tiles(unsigned long long* __restrict__ tile_sum, unsigned int ntiles,
+                           unsigned long long* __restrict__ total) {
+  // single block, sequential over chunks of blockDim tiles (ntiles is a few thousand at most)
+  __shared__ unsigned long long s_v[1024];
+  __shared__ unsigned long long s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (unsigned int b = 0; b < ntiles; b += blockDim.x) {
+    const unsigned int i = b + threadIdx.x;
+    const unsigned long long v = (i < ntiles) ? tile_sum[i] : 0ull;
+    s_v[threadIdx.x] = v;
+    __syncthreads();
+    for (unsigned int d = 1; d < blockDim.x; d <<= 1) {              // Hillis-Steele inclusive scan
+      const unsigned long long a = (threadIdx.x >= d) ? s_v[threadIdx.x - d] : 0ull;
+      __syncthreads();
+      s_v[threadIdx.x] += a;
+      __syncthreads();
+    }
+    if (i < ntiles) tile_sum[i] = s_carry + s_v[threadIdx.x] - v;    // exclusive
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) s_carry += s_v[threadIdx.x];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = s_carry;
+}
+
+__global__ void scan_apply(const unsigned int* __restrict__ nev, unsigned long long n,
+                           const unsigned long long* __restrict__ tile_off, unsigned long long* __restrict__ offsets) {
+  // one thread handles kScanItems CONSECUTIVE electrons; block-level exclusive scan of the thread sums
+  __shared__ unsigned long long s_w[kScanT / 32];
+  const unsigned long long base = (unsigned long long)blockIdx.x * kScanT * kScanItems + (unsigned long long)threadIdx.x * kScanItems;
+  unsigned int loc[kScanItems];
+  unsigned long long sum = 0;
+  for (int k = 0; k < kScanItems; ++k) {
+    loc[k] = (base + k < n) ? nev[base + k] : 0u;
+    sum += loc[k];
+  }
+  unsigned long long incl = sum;
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned long long o = __shfl_up_sync(MCD_FULL_MASK, incl, d);
+    if (lane >= (unsigned)d) incl += o;
+  }
+  if (lane == 31) s_w[warp] = incl;
+  __syncthreads();
+  unsigned long long woff = 0;
+  for (unsigned w = 0; w < warp; ++w) woff += s_w[w];
+  unsigned long long run = tile_off[blockIdx.x] + woff + incl - sum;
+  for (int k = 0; k < kScanItems; ++k) {
+    if (base + k < n) offsets[base + k] = run;
+    run += loc[k];
+  }
+  if (base <= n && n < base + kScanItems) offsets[n] = run - 0;       // offsets[n] = total (set by the owner of n)
+}
+
+// every stored row of the chunk pool goes to sorted[offsets[rel_id] + event]
+__global__ void scatter_rows(const uint32_t* __restrict__ pool, const unsigned int* __restrict__ chunk_count,
+                             unsigned int nchunks, int row_words, const unsigned long long* __restrict__ offsets,
+                             uint32_t* __restrict__ sorted) {
+  for (unsigned int c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    const unsigned int cnt = chunk_count[c];
+    for (unsigned int r = threadIdx.x; r < cnt; r += blockDim.x) {
+      const uint32_t* src = pool + ((size_t)c * MCD_CHUNK_ROWS + r) * (size_t)row_words;
+      const uint32_t rel = src[0], w1 = src[1];
+      uint32_t* dst = sorted + (offsets[rel] + (unsigned long long)(w1 & 0xffffffu)) * (unsigned long long)row_words;
+      dst[0] = rel;
+      dst[1] = w1;
+      for (int w = 2; w < row_words; ++w) dst[w] = src[w];
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t mcd_launch_order_scats(const unsigned int* nev, unsigned long long count, unsigned long long* tile_tmp,
+                                   unsigned long long* offsets, unsigned long long* total_dev, const uint32_t* pool,
+                                   const unsigned int* chunk_count, unsigned int nchunks, int row_words,
+                                   uint32_t* sorted, int sm_count, cudaStream_t stream) {
+  const unsigned long long per_tile = (unsigned long long)kScanT * kScanItems;
+  const unsigned int ntiles = (unsigned int)((count + 1 + per_tile - 1) / per_tile);
+  scan_tile_sums<<<ntiles, kScanT, 0, stream>>>(nev, count, tile_tmp);
+  scan_tiles<<<1, 1024, 0, stream>>>(tile_tmp, ntiles, total_dev);
+  scan_apply<<<ntiles, kScanT, 0, stream>>>(nev, count, tile_tmp, offsets);
+  if (sorted && nchunks) scatter_rows<<<sm_count * 8, 256, 0, stream>>>(pool, chunk_count, nchunks, row_words, offsets, sorted);
+  return cudaGetLastError();
+}
+
+unsigned long long mcd_order_tiles(unsigned long long count) {
+  const unsigned long long per_tile = (unsigned long long)kScanT * kScanItems;
+  return (count + 1 + per_tile - 1) / per_tile;
+}
 
 cudaError_t mcd_traj_max_blocks(const DevParams& P, int sm_count, TrajLaunchInfo* info) {
   TrajKernel k = pick_kernel(P);

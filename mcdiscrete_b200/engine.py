@@ -33,8 +33,9 @@ class ScatRows:
     _FLOAT = {1: 'position', 2: 'pathl', 3: 'E', 4: 'E_loss', 5: 'pol_angle', 6: 'az_angle', 7: 'energy',
               8: 'direction'}
 
-    def __init__(self, words, word_of, first_id):
+    def __init__(self, words, word_of, first_id, offsets=None):
         self.words, self.word_of, self.first_id = words, word_of, int(first_id)
+        self.offsets = offsets        # set when the rows are in trajectory order: electron i owns rows offsets[i]:offsets[i+1]
         self._cache = {}
         self._names = ['el', 'ev']
         if word_of[0] >= 0:
@@ -104,11 +105,12 @@ class RunResult:
 
     def sorted_scats(self):
         """scats columns regrouped per electron in event order (the reference's row order)."""
-        if not len(self.scats):
+        if not len(self.scats) or self.scats.offsets is not None:
             return self.scats
         w = self.scats.words
         order = np.lexsort((w[:, 1] & 0xffffff, w[:, 0]))
-        return ScatRows(w[order], self.scats.word_of, self.scats.first_id)
+        off = np.concatenate([[0], np.cumsum(np.bincount(w[:, 0].astype(np.int64), minlength=self.count))]).astype(np.uint64)
+        return ScatRows(w[order], self.scats.word_of, self.scats.first_id, off)
 
 
 class Engine:
@@ -303,8 +305,9 @@ class Engine:
         self._ck(self.lib.mcd_launch_info(self.ctx, C.byref(b), C.byref(t), C.byref(r), C.byref(o)))
         return {'blocks': b.value, 'threads': t.value, 'regs': r.value, 'blocks_per_sm': o.value}
 
-    def drain(self, first_id, count, want_els=True, want_scats=True, pinned=False, stream=None):
-        """Copy the rows of the last run to host arrays."""
+    def drain(self, first_id, count, want_els=True, want_scats=True, pinned=False, stream=None, ordered=False):
+        """Copy the rows of the last run to host arrays.  ordered=True regroups the scats rows on the device
+        into trajectory order first (mcd_order_scats) and returns them with per-electron offsets."""
         st = C.c_void_p(stream or 0)
         n_els, n_sc = C.c_uint64(), C.c_uint64()
         self._ck(self.lib.mcd_row_counts(self.ctx, C.byref(n_els), C.byref(n_sc)))
@@ -318,15 +321,21 @@ class Engine:
         words = None
         if want_scats and self.row_words and self.cap_sc:
             rawb = self._host('scats', nsc * self.row_words * 4, pinned)
-            if nsc:
+            offs = None
+            if nsc and ordered:
+                self._ck(self.lib.mcd_order_scats(self.ctx, st))
+                self._ck(self.lib.mcd_drain_scats_ordered(self.ctx, rawb.ctypes.data_as(C.c_void_p), 0, nsc, st))
+                offs = self._host('offsets', (count + 1) * 8, pinned).view(np.uint64)
+                self._ck(self.lib.mcd_scat_offsets(self.ctx, offs.ctypes.data_as(C.POINTER(C.c_uint64)), 0, count, st))
+            elif nsc:
                 self._ck(self.lib.mcd_drain_scats(self.ctx, rawb.ctypes.data_as(C.c_void_p), 0, nsc, st))
             words = rawb.view(np.uint32).reshape(nsc, self.row_words)
         self.sync(stream)
         if words is not None:
-            scats = ScatRows(words, self.word_of, first_id)
+            scats = ScatRows(words, self.word_of, first_id, offs)
         return els, scats
 
-    def run(self, count=None, first_id=None, max_scat_rows=None, pinned=False, stream=None, drain=True):
+    def run(self, count=None, first_id=None, max_scat_rows=None, pinned=False, stream=None, drain=True, ordered=False):
         """Simulate `count` electrons (default inputPar['num_el']) with ids starting at `first_id`
         (default: continue after the previous run) and return a RunResult."""
         count = int(count if count is not None else self.inputPar['num_el'])
@@ -354,10 +363,10 @@ class Engine:
                                     'fewer electrons per batch' % (cnt['scat_rows_dropped'], self.cap_sc))
             max_scat_rows = min(2 * self.cap_sc, count * int(self.inputPar['maxScatt']))
         self.next_id = max(self.next_id, first_id + count)
-        els, scats = self.drain(first_id, count, pinned=pinned, stream=stream) if drain else (None, {})
+        els, scats = self.drain(first_id, count, pinned=pinned, stream=stream, ordered=ordered) if drain else (None, {})
         return RunResult(first_id, count, els, scats, cnt, self.kernel_ms())
 
-    def run_batches(self, total, batch, first_id=0, max_scat_rows=None, on_launched=None):
+    def run_batches(self, total, batch, first_id=0, max_scat_rows=None, on_launched=None, ordered=False):
         """Simulate `total` electrons in batches of `batch`, PIPELINED over two contexts / two CUDA streams:
         while the host drains batch k (D2H into pinned buffers) batch k+1 already runs, and its blocks fill the
         SMs that the tail of batch k leaves idle.  Yields one RunResult per batch, in order.  Rows of a yielded
@@ -380,7 +389,7 @@ class Engine:
             cnts = e.counters()
             if cnts['scat_rows_dropped']:
                 raise _lib.MCDError(-5, '%d scats rows did not fit: raise max_scat_rows or lower batch' % cnts['scat_rows_dropped'])
-            els, scats = e.drain(first, cnt, pinned=True, stream=st)
+            els, scats = e.drain(first, cnt, pinned=True, stream=st, ordered=ordered)
             return RunResult(first, cnt, els, scats, cnts, e.kernel_ms())
         k = 0
         try:

@@ -73,7 +73,7 @@ def _per_electron_dicts(eng, res, inputPar, thingsToSave):
     n = res.count
     have_sc = len(sc) > 0
     if have_sc:
-        bounds = np.searchsorted(sc['el'], np.arange(res.first_id, res.first_id + n + 1))
+        bounds = sc.offsets.astype(np.int64)
     double = bool(inputPar.get('reference_double_record', False))
     out = []
     for i in range(n):
@@ -114,7 +114,7 @@ def _per_electron_dicts(eng, res, inputPar, thingsToSave):
 def multiTraj_DS(inputPar, numTraj, material, tables, thingsToSave):
     """multiScatter.py:66-116."""
     eng = _engine_for(inputPar, material, thingsToSave, tables)
-    res = eng.run(count=numTraj)
+    res = eng.run(count=numTraj, ordered=True)
     return _per_electron_dicts(eng, res, inputPar, thingsToSave)
 
 
@@ -123,7 +123,7 @@ def multiTraj_cont(inputPar, numTraj, material, thingsToSave, tables):
     if inputPar.get('Bethe_model', 'classical') not in _lib.BETHE:
         raise SystemExit('! I did not understand your choice of Bethe model in multiScatter')
     eng = _engine_for(inputPar, material, thingsToSave, None)
-    res = eng.run(count=numTraj)
+    res = eng.run(count=numTraj, ordered=True)
     return _per_electron_dicts(eng, res, inputPar, thingsToSave)
 
 

@@ -481,3 +481,30 @@ def test_pipelined_batches_equal_single_run():
     assert np.array_equal(np.concatenate(parts), els_whole)
     assert ev == ev_whole == nrows
     eng.close()
+
+
+def test_device_regrouping_of_scats_rows():
+    """mcd_order_scats: rows regrouped on the device into the reference's order == host lexsort of the appended rows."""
+    eng = make_engine(Emin=15000.)
+    upload_golden(eng, golden_tables('Si_15k_small'))
+    N = 30000
+    a = eng.run(count=N, first_id=500)
+    host = a.sorted_scats()
+    hw = host.words.copy()
+    hoff = host.offsets.copy()
+    b = eng.run(count=N, first_id=500, ordered=True)
+    assert b.scats.offsets is not None and b.sorted_scats() is b.scats
+    assert np.array_equal(b.scats.offsets, hoff)
+    assert np.array_equal(b.scats.words, hw)
+    nev = np.diff(b.scats.offsets.astype(np.int64))
+    assert nev.sum() == len(b.scats) == b.counters['events']
+    k = int(np.argmax(nev))
+    lo, hi = int(b.scats.offsets[k]), int(b.scats.offsets[k + 1])
+    assert (b.scats['el'][lo:hi] == 500 + k).all() and np.array_equal(b.scats['ev'][lo:hi], np.arange(hi - lo))
+    # pipelined batches with device regrouping
+    tot = 0
+    for r in eng.run_batches(N, 11000, first_id=500, ordered=True):
+        assert r.scats.offsets[-1] == len(r.scats)
+        tot += len(r.scats)
+    assert tot == len(b.scats)
+    eng.close()
