@@ -41,15 +41,30 @@ MUFU_PER_EVENT = 11 + 3 * N_SHELLS
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md): NVML polled every 5 ms from
+    a thread (nvidia-smi -lms cannot deliver more than a sample or two inside a 100 ms region); nvidia-smi is the
+    fallback when NVML is unavailable."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
+    BITS = {'hw_slowdown': 0x8, 'hw_thermal_slowdown': 0x40, 'sw_thermal_slowdown': 0x20, 'sw_power_cap': 0x4}
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml, self._stop = index, [], None, None, False
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = int(vis.split(',')[self.index]) if vis and vis.split(',')[self.index].isdigit() else self.index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            threading.Thread(target=self._poll, daemon=True).start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
                                           '--format=csv,noheader,nounits', '-lms', '20'],
@@ -58,11 +73,35 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self._stop:
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+                try:
+                    reasons = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    reasons = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                pw = n.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                self.rows.append((time.time(), mhz, reasons, pw))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.time(), [x.strip() for x in line.split(',')]))
 
     def stop(self, t0, t1):
+        if self.nvml is not None:
+            self._stop = True
+            rows = [r for r in self.rows if t0 <= r[0] <= t1] or self.rows[-3:]
+            if not rows:
+                return {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'reasons': ['no samples']}
+            sm = sorted(r[1] for r in rows)
+            reasons = sorted(k for k, b in self.BITS.items() if any(r[2] & b for r in rows))
+            return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': self.max_mhz, 'reasons': reasons, 'samples': len(rows),
+                    'power_w_max': max(r[3] for r in rows), 'source': 'nvml, 5 ms polling inside the timed region'}
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         time.sleep(0.15)
@@ -77,7 +116,7 @@ class ClockSampler:
                 if v.lower().startswith('active'):
                     reasons.add(name)
         return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(rows[0][2]), 'reasons': sorted(reasons),
-                'samples': len(rows), 'power_w_max': max(float(r[3]) for r in rows)}
+                'samples': len(rows), 'power_w_max': max(float(r[3]) for r in rows), 'source': 'nvidia-smi -lms 20'}
 
 
 def cpu_sample(n_el, nthreads, tables=None):
@@ -271,7 +310,11 @@ def main():
                          'ops_per_event': MUFU_PER_EVENT},
                 'peak_source': 'measured on this GPU by mcd_measure_peaks (FFMA / MUFU.EX2 dependent chains); '
                                'MEASURED_PEAKS.json has no FP32/MUFU figure',
-                'hbm': {'table_bytes_resident': table_bytes, 'peak_gbs_measured': 6547.2}}
+                'hbm': {'table_bytes_resident': table_bytes, 'peak_gbs_measured': 6547.2,
+                        'achieved_gbs': (traffic / (k_ms * 1e-3) / 1e9) if traffic else None,
+                        'frac': (traffic / (k_ms * 1e-3) / 1e9 / 6547.2) if traffic else None,
+                        'note': 'DRAM traffic of the trajectory kernel (ncu) over its CUDA-event duration; the kernel is '
+                                'issue-bound, HBM is second order'}}
 
     # ---- end to end through the public API with pinned host outputs ------------------------------------------
     h2d = C.sizeof(_lib.Params) + 1024      # launch parameter block: there are no per-step input arrays
