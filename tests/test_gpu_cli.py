@@ -65,3 +65,49 @@ def test_workers_with_reference_signatures():
     resc = multiTraj_cont(ipc, 4, material('Si'), whatc, {})      # multiScatter.py:171 argument order
     assert len(resc) == 4 and resc[0]['scats']['type'][0] == 'Ruth_vanilla'
     assert len(resc[0]['scats']['pathl']) == len(resc[0]['scats']['energy'])
+
+
+def test_error_behaviour_and_legacy_wrappers():
+    """Status codes instead of crashes (include/mcd.h conventions) and the legacy process targets."""
+    import queue
+    from mcdiscrete_b200 import _lib
+    from mcdiscrete_b200.engine import Engine
+    from mcdiscrete_b200 import genTables, scatterMultiEl_DS, scatterMultiEl_cont
+    ip = dict(num_el=6, E0=20000., Emin=15000., material='Si', s_tilt=70., thickness=3e6, elastic='Ruth_vanilla',
+              mode='DS', Bethe_model='classical', diffMFP=False, gen_tables=True, tol_E=1e-2, tol_W=1e-3,
+              maxScatt=1000, Wc=10., electron_output=['outcome', 'final_E'], scatter_output=['type', 'energy'])
+    eng = Engine(ip, device=0)
+    eng.set_capacity(10, 1000)
+    with pytest.raises(_lib.MCDError) as ei:                      # DS run without tables
+        eng.launch(0, 10)
+    assert ei.value.code == -4 and 'table' in str(ei.value)
+    with pytest.raises(_lib.MCDError) as ei:                      # more electrons than the capacity
+        genTables(ip, engine=eng)
+        eng.launch(0, 11)
+    assert ei.value.code == -1
+    # too small a scats pool: explicit capacity -> error with the dropped-row count; automatic capacity regrows
+    # (the pool always holds one spare chunk per resident warp, ~4.8e6 rows: overflow needs more rows than that)
+    with pytest.raises(_lib.MCDError) as ei:
+        eng.run(count=40000, first_id=0, max_scat_rows=1000)
+    assert ei.value.code == -5
+    res = eng.run(count=40000, first_id=0)
+    assert res.counters['scat_rows_dropped'] == 0 and len(res.scats) == res.counters['events']
+    with pytest.raises(ValueError):
+        Engine(dict(ip, scatter_output=['nonsense']), device=0)
+    with pytest.raises(NotImplementedError):
+        Engine(dict(ip, elastic='Mott'), device=0)
+    with pytest.raises(_lib.MCDError):                            # Emin below the plasmon energy (quinn_sigma :272-281)
+        Engine(dict(ip, Emin=10.), device=0)
+    eng.close()
+    # legacy targets (multiScatter.py:15-61, 118-168)
+    tables = genTables(ip)
+    what = {'el_output': ip['electron_output'], 'scat_output': ip['scatter_output']}
+    out = {}
+    scatterMultiEl_DS(ip, tables, what, out, 0)
+    assert set(out) == {'els', 'scats'} and len(out['els']['outcome']) >= 1
+    q = {'electrons': queue.Queue(), 'scatterings': queue.Queue()}
+    ipc = dict(ip, mode='cont', Emin=500., scatter_output=['type', 'energy'])
+    scatterMultiEl_cont(ipc, {'el_output': ip['electron_output'], 'scat_output': ipc['scatter_output']}, q, 5, 0)
+    import pickle
+    els = pickle.loads(q['electrons'].get())
+    assert len(els['outcome']) == 5 and len(pickle.loads(q['scatterings'].get())['energy']) > 5
