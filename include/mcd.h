@@ -219,6 +219,12 @@ int mcd_measure_peaks(int device, float* fp32_tflops, float* mufu_tops, float* s
 /* ---- unit hooks (injected uniforms; all arrays are HOST pointers, n vectors) --------------- */
 /* sigma_out: n x (S+3) in sigma insertion order, cm^2; mfp_out: total mean free path in Angstrom. */
 int mcd_test_sigmas(mcd_ctx* ctx, const float* E, uint64_t n, float* sigma_out, float* mfp_out);
+/* The cumulative inverse mean free paths (1/Angstrom) the hot path uses for the channel pick and the path length,
+ * in SLOT order (descending sigma: Ruth, Quinn, Moller, Gryzinski shells): cum_out is n x (S+3);
+ * slot_channel_out[S+3] maps slots to sigma insertion indices; *uses_poly = 1 when they come from the per-cell
+ * quadratics built at mcd_create (else from the formulas), *poly_err = their verified worst error / total. */
+int mcd_test_cum(mcd_ctx* ctx, const float* E, uint64_t n, float* cum_out, int32_t* slot_channel_out,
+                 int32_t* uses_poly, double* poly_err);
 /* pickFromSigmas on given sigmas (n x nch, insertion order): pick_out = insertion index;
  * path_out (optional) = 0 fast float32 path, 1 exact float64 path. */
 int mcd_test_select(mcd_ctx* ctx, const float* sigma, int nch, const float* u, uint64_t n,

@@ -93,6 +93,7 @@ SYMBOLS = {
     'mcd_launch_info': (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     'mcd_measure_peaks': (C.c_int, [C.c_int, _F, _F, _F]),
     'mcd_test_sigmas': (C.c_int, [_P, _F, _U64, _F, _F]),
+    'mcd_test_cum': (C.c_int, [_P, _F, _U64, _F, _I, _I, C.POINTER(C.c_double)]),
     'mcd_test_select': (C.c_int, [_P, _F, C.c_int, _F, _U64, _I, _I]),
     'mcd_test_ruth': (C.c_int, [_P, _F, _F, _U64, _F, _F]),
     'mcd_test_bincoll': (C.c_int, [_P, _F, _F, _U64, _F, _F]),

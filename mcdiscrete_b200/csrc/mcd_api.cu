@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include <new>
 #include <string>
@@ -38,6 +39,9 @@ struct mcd_ctx {
   DevParams P;
   HostTable tab[MCD_MAX_TABLES];
   bool owns_tables = true;
+  float4* sig_poly = nullptr;                 // per-cell quadratics of the cumulative cross-sections
+  double sig_poly_err = 0.0;                  // verified max error relative to the total
+  int slot_order[MCD_MAX_SHELLS] = {0};
   // outputs
   mcd_el_row* els = nullptr;
   uint64_t max_el = 0;
@@ -129,6 +133,88 @@ int order_is_static(const mcd_params& p, const mcd_material& mt, const int* orde
   return 1;
 }
 
+// cumulative inverse mean free paths (1/Angstrom) in slot order at energy E, float64
+void cum_host(const mcd_params& p, const mcd_material& mt, const int* order, double E, double* cum) {
+  const double scale = mt.atnd * 1e-14;
+  double c = ruth_sigma_host(E, mt.Z) * scale;
+  cum[0] = c;
+  c += quinn_sigma_host(E, mt.plasmon_e, mt.fermi_e, mt.atnd) * scale;
+  cum[1] = c;
+  c += moller_sigma_host(E, p.Wc, mt.n_val) * scale;
+  cum[2] = c;
+  for (int k = 0; k < mt.n_shells; ++k) {
+    c += gryz_sigma_host(E, mt.shell_E[order[k]], mt.shell_n[order[k]]) * scale;
+    cum[3 + k] = c;
+  }
+}
+
+// Per-cell quadratics of cum_k(E): octaves [2^e, 2^(e+1)) cut into 2^logM cells, coordinate x in [0,1) inside a
+// cell; interpolation at the three Chebyshev nodes of [0,1], verified on 7 further points per cell.  logM is raised
+// until the worst error is below 1.5e-7 of the total (else the kernel keeps evaluating the formulas).
+int build_sig_poly(mcd_ctx* c, const int* order) {
+  const mcd_params& p = c->par;
+  const mcd_material& mt = c->mat;
+  const int nch = mt.n_shells + 3;
+  int e_min, e_max;
+  frexp(p.Emin * 0.999, &e_min); e_min -= 1;               // 2^e_min <= 0.999 Emin
+  frexp(p.E0, &e_max); e_max -= 1;                         // 2^e_max <= E0 < 2^(e_max+1)
+  if (e_min < 1 || e_max > 30) return 0;
+  const double node[3] = {0.5 - 0.25 * sqrt(3.0), 0.5, 0.5 + 0.25 * sqrt(3.0)};
+  for (int logM = 7; logM <= 11; ++logM) {
+    const int M = 1 << logM;
+    const int ncell = (e_max - e_min + 1) * M;
+    std::vector<float4> poly((size_t)ncell * nch);
+    double worst = 0.0;
+    for (int cell = 0; cell < ncell; ++cell) {
+      const double Ea = ldexp(1.0 + (double)(cell % M) / M, e_min + cell / M);
+      const double dEc = ldexp(1.0 / M, e_min + cell / M);
+      double f[3][MCD_MAX_CHANNELS];
+      if (Ea + dEc <= mt.plasmon_e * 1.001) {                // below the Quinn threshold: never visited
+        for (int k = 0; k < nch; ++k) poly[(size_t)cell * nch + k] = make_float4(1.f, 0.f, 0.f, 0.f);
+        continue;
+      }
+      for (int i = 0; i < 3; ++i) cum_host(p, mt, order, fmax(Ea + node[i] * dEc, mt.plasmon_e * 1.001), f[i]);
+      for (int k = 0; k < nch; ++k) {
+        // Newton form through (node_i, f_i) expanded to c0 + c1 x + c2 x^2
+        const double d01 = (f[1][k] - f[0][k]) / (node[1] - node[0]);
+        const double d12 = (f[2][k] - f[1][k]) / (node[2] - node[1]);
+        const double c2 = (d12 - d01) / (node[2] - node[0]);
+        const double c1 = d01 - c2 * (node[0] + node[1]);
+        const double c0 = f[0][k] - node[0] * (d01 - c2 * node[1]);
+        poly[(size_t)cell * nch + k] = make_float4((float)c0, (float)c1, (float)c2, 0.f);
+      }
+      if (Ea + dEc < p.Emin * 0.999 || Ea > p.E0 * 1.001) continue;       // outside the visited range
+      for (int j = 0; j < 7; ++j) {
+        const double x = (j + 0.5) / 7.0;
+        double ref[MCD_MAX_CHANNELS];
+        const double E = Ea + x * dEc;
+        if (E <= mt.plasmon_e * 1.001) continue;
+        cum_host(p, mt, order, E, ref);
+        for (int k = 0; k < nch; ++k) {
+          const float4 q = poly[(size_t)cell * nch + k];
+          const float xf = (float)x;
+          const double got = (double)fmaf(fmaf(q.z, xf, q.y), xf, q.x);
+          worst = fmax(worst, fabs(got - ref[k]) / ref[nch - 1]);
+        }
+      }
+    }
+    if (worst < 1.5e-7) {
+      cudaFree(c->sig_poly); c->sig_poly = nullptr;
+      if (cudaMalloc(&c->sig_poly, poly.size() * sizeof(float4)) != cudaSuccess) return 0;
+      if (cudaMemcpy(c->sig_poly, poly.data(), poly.size() * sizeof(float4), cudaMemcpyHostToDevice) != cudaSuccess) return 0;
+      DevParams& P = c->P;
+      P.sig_poly = c->sig_poly;
+      P.sig_shift = 23 - logM;
+      P.sig_base = (uint32_t)(((uint32_t)(e_min + 127) << 23) >> P.sig_shift);
+      P.sig_ncell = ncell;
+      P.sig_nch = nch;
+      c->sig_poly_err = worst;
+      return 1;
+    }
+  }
+  return 0;
+}
+
 void build_dev_params(mcd_ctx* c) {
   const mcd_params& p = c->par;
   const mcd_material& mt = c->mat;
@@ -201,6 +287,7 @@ void build_dev_params(mcd_ctx* c) {
     P.pkey[2 * r + 1] = P.seed_hi + (uint32_t)r * 0xBB67AE85u;
   }
   P.order_static = (p.mode == MCD_MODE_DS) ? order_is_static(p, mt, order) : 0;
+  memcpy(c->slot_order, order, sizeof(int) * MCD_MAX_SHELLS);
   P.scat_mask = p.scat_mask;
   P.flags = p.flags;
   // histogram axes: energy [Emin,E0], depth [0, 2R], R = E0 / S_Bethe,classical(E0)
@@ -358,6 +445,9 @@ int mcd_create(const mcd_params* p, const mcd_material* m, int device, mcd_ctx**
   if (e != cudaSuccess) { delete c; return fail(nullptr, MCD_ERR_CUDA, "props: %s", cudaGetErrorString(e)); }
   c->sm_count = pr.multiProcessorCount;
   build_dev_params(c);
+  c->P.use_sig_poly = 0;
+  if (p->mode == MCD_MODE_DS && c->P.order_static && !getenv("MCD_NO_SIGPOLY"))
+    c->P.use_sig_poly = build_sig_poly(c, c->slot_order);
   mcd_scat_layout L;
   layout_of(p->scat_mask, &L);
   c->P.scat_row_words = (int)L.row_words;
@@ -415,6 +505,7 @@ int mcd_destroy(mcd_ctx* c) {
   if (!c) return MCD_OK;
   cudaSetDevice(c->device);
   if (c->owns_tables) for (auto& t : c->tab) free_table(t);
+  if (c->owns_tables) cudaFree(c->sig_poly);
   cudaFree(c->els); cudaFree(c->scats); cudaFree(c->chunk_next); cudaFree(c->chunk_count); cudaFree(c->ticket);
   cudaFree(c->nev); cudaFree(c->sorted); cudaFree(c->offsets); cudaFree(c->tile_tmp); cudaFree(c->total_dev);
   cudaFree(c->stats);
@@ -755,6 +846,26 @@ int mcd_test_sigmas(mcd_ctx* c, const float* E, uint64_t n, float* sigma_out, fl
   CU(c, dE.up(E, n)); CU(c, dS.alloc(n * nch)); CU(c, dM.alloc(n));
   CU(c, mcd_launch_test_sigmas(c->P, dE.p, n, dS.p, dM.p, 0));
   CU(c, dS.down(sigma_out, n * nch)); CU(c, dM.down(mfp_out, n));
+  return MCD_OK;
+}
+
+int mcd_test_cum(mcd_ctx* c, const float* E, uint64_t n, float* cum_out, int32_t* slot_channel_out,
+                 int32_t* uses_poly, double* poly_err) {
+  int rc = need_ctx(c);
+  if (rc) return rc;
+  const int nch = c->mat.n_shells + 3;
+  if (n) {
+    Tmp<float> dE, dC;
+    CU(c, dE.up(E, n)); CU(c, dC.alloc(n * nch));
+    CU(c, mcd_launch_test_cum(c->P, dE.p, n, dC.p, 0));
+    CU(c, dC.down(cum_out, n * nch));
+  }
+  if (slot_channel_out) {
+    slot_channel_out[0] = 0; slot_channel_out[1] = 2 + c->mat.n_shells; slot_channel_out[2] = 1;
+    for (int k = 0; k < c->mat.n_shells; ++k) slot_channel_out[3 + k] = 2 + c->P.m.gShell[k];
+  }
+  if (uses_poly) *uses_poly = c->P.use_sig_poly;
+  if (poly_err) *poly_err = c->sig_poly_err;
   return MCD_OK;
 }
 

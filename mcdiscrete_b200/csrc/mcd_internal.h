@@ -42,6 +42,7 @@ cudaError_t mcd_launch_table_guide(const float* cdf, int nE, int nW, const int* 
 // mcd_unit.cu
 cudaError_t mcd_launch_test_sigmas(const DevParams& P, const float* E, uint64_t n, float* sig, float* mfp,
                                    cudaStream_t s);
+cudaError_t mcd_launch_test_cum(const DevParams& P, const float* E, uint64_t n, float* cum, cudaStream_t s);
 cudaError_t mcd_launch_test_select(const float* sigma, int nch, const float* u, uint64_t n, int* pick, int* path,
                                    cudaStream_t s);
 cudaError_t mcd_launch_test_ruth(const DevParams& P, const float* E, const float* u, uint64_t n, float* c2,

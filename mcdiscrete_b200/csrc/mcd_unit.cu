@@ -41,6 +41,37 @@ __global__ void k_sigmas(const __grid_constant__ DevParams P, const float* E, ui
   mfp[i] = 1.0f / tot;
 }
 
+// the hot path's cumulative inverse mean free paths in slot order (per-cell quadratics when enabled)
+__global__ void k_cum(const __grid_constant__ DevParams P, const float* E, uint64_t n, float* cum_out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int nch = P.m.nshell + 3;
+  const float e = E[i];
+  if (P.use_sig_poly) {
+    const uint32_t bits = __float_as_uint(e);
+    const uint32_t cell = min((bits >> P.sig_shift) - P.sig_base, (uint32_t)(P.sig_ncell - 1));
+    const float x = (float)(bits & ((1u << P.sig_shift) - 1u)) * __uint_as_float((uint32_t)(127 - P.sig_shift) << 23);
+    const float4* q = P.sig_poly + (size_t)cell * (size_t)nch;
+    for (int k = 0; k < nch; ++k) {
+      const float4 c = __ldg(q + k);
+      cum_out[i * nch + k] = fmaf(fmaf(c.z, x, c.y), x, c.x);
+    }
+  } else {
+    const DevMat& m = P.m;
+    const float invE = f_rcp(e);
+    float c = s_ruth(m, e);
+    cum_out[i * nch + 0] = c;
+    c += s_quinn(m, e, invE);
+    cum_out[i * nch + 1] = c;
+    c += s_moller(m, e, invE);
+    cum_out[i * nch + 2] = c;
+    for (int k = 0; k < m.nshell; ++k) {
+      c += s_gryz(e, invE, m.gE[k], m.gInvE[k], m.gC[k]);
+      cum_out[i * nch + 3 + k] = c;
+    }
+  }
+}
+
 // pickFromSigmas on arbitrary sigmas: mirrors the trajectory kernel's decision structure -- the fast
 // float32 path is taken only when the values are already in strictly descending order (zeros allowed at
 // the tail) and u*total is outside the guard band of every boundary; otherwise the exact float64 path.
@@ -189,6 +220,9 @@ inline int nblk(uint64_t n) { return (int)((n + kT - 1) / kT); }
 
 cudaError_t mcd_launch_test_sigmas(const DevParams& P, const float* E, uint64_t n, float* sig, float* mfp,
                                    cudaStream_t s) { LAUNCH(k_sigmas, n, s, P, E, n, sig, mfp); }
+cudaError_t mcd_launch_test_cum(const DevParams& P, const float* E, uint64_t n, float* cum, cudaStream_t s) {
+  LAUNCH(k_cum, n, s, P, E, n, cum);
+}
 cudaError_t mcd_launch_test_select(const float* sigma, int nch, const float* u, uint64_t n, int* pick, int* path,
                                    cudaStream_t s) { LAUNCH(k_select, n, s, sigma, nch, u, n, pick, path); }
 cudaError_t mcd_launch_test_ruth(const DevParams& P, const float* E, const float* u, uint64_t n, float* c2,

@@ -422,6 +422,16 @@ class Engine:
         self._ck(self.lib.mcd_test_sigmas(self.ctx, fptr(E), len(E), fptr(sig), fptr(mfp)))
         return sig, mfp
 
+    def test_cum(self, E):
+        """(cum[n, S+3] in slot order, slot->channel map, uses_poly, verified poly error)"""
+        E = f32(E)
+        nch = self.cmat.n_shells + 3
+        cum = np.empty((len(E), nch), np.float32)
+        sl = np.empty(nch, np.int32)
+        up, err = C.c_int32(), C.c_double()
+        self._ck(self.lib.mcd_test_cum(self.ctx, fptr(E), len(E), fptr(cum), iptr(sl), C.byref(up), C.byref(err)))
+        return cum, sl, bool(up.value), err.value
+
     def test_select(self, sigma, u):
         sigma, u = f32(sigma), f32(u)
         pick = np.empty(len(u), np.int32)

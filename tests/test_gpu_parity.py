@@ -508,3 +508,22 @@ def test_device_regrouping_of_scats_rows():
         tot += len(r.scats)
     assert tot == len(b.scats)
     eng.close()
+
+
+@pytest.mark.parametrize('name,E0,Emin', [('Si', 20000., 10000.), ('Cu', 20000., 10000.), ('Au', 30000., 15000.),
+                                          ('Al', 30000., 2600.)])
+def test_cumulative_cross_sections_of_the_hot_path(name, E0, Emin):
+    """The cumulative inverse mean free paths the trajectory kernel uses (per-cell quadratics built and verified at
+    mcd_create) against the float64 formulas: every boundary within 3e-7 of the total."""
+    eng = make_engine(material=name, E0=E0, Emin=Emin)
+    m = o.Material(name)
+    rng = np.random.default_rng(9)
+    E = np.concatenate([rng.uniform(Emin, E0, 20000), [E0, Emin * 1.00001], np.geomspace(Emin * 1.0001, E0, 3000)]).astype(np.float32)
+    cum, slot_ch, uses_poly, err = eng.test_cum(E)
+    assert uses_poly and err < 1.5e-7
+    assert slot_ch[0] == 0 and slot_ch[1] == len(m.Es) + 2 and slot_ch[2] == 1
+    scale = m.atnd * 1e-14
+    ref = np.array([np.cumsum(np.array(o.sigmas_ds(float(e), m, 10.))[slot_ch]) * scale for e in E])
+    assert (np.abs(cum - ref) / ref[:, -1:]).max() < 3e-7
+    assert (np.diff(cum, axis=1) >= 0).all()
+    eng.close()
