@@ -18,9 +18,12 @@
 
 namespace {
 
-constexpr int kThreads = 256;
+#ifndef MCD_THREADS
+#define MCD_THREADS 192
+#endif
+constexpr int kThreads = MCD_THREADS;
 #ifndef MCD_MIN_BLOCKS
-#define MCD_MIN_BLOCKS 4          // resident blocks per SM the register allocation is held to (64 regs)
+#define MCD_MIN_BLOCKS 6          // 6 x 192 threads = 36 warps per SM at 56 registers (measured best: r1h notes)
 #endif
 constexpr int kCntOutcome = 0;       // 5
 constexpr int kCntEvents = 5;
