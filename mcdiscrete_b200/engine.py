@@ -185,10 +185,12 @@ class Engine:
         other._pinned = {}
         other._parent = self                      # keep the owner of the tables alive
         other._clones = []
+        other._pipe = None
         self._clones = getattr(self, '_clones', []) + [other]
         return other
 
     def close(self):
+        self._pipe = None
         for c in getattr(self, '_clones', []):    # clones first: they borrow this context's tables
             c.close()
         self._clones = []
@@ -377,8 +379,14 @@ class Engine:
         if self.params.mode == _lib.MODE_DS and self.tables is None:
             from .probTables import genTables
             genTables(self.inputPar, engine=self)
-        engs = [self, self.clone()]
-        streams = [torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device)]
+        # the second context, its device buffers, the pinned staging buffers and the two streams are kept for
+        # later calls (creating them costs tens of milliseconds of cudaMalloc / page-locking)
+        pipe = getattr(self, '_pipe', None)
+        if pipe is None:
+            pipe = self._pipe = (self.clone(), [torch.cuda.Stream(device=self.device),
+                                                torch.cuda.Stream(device=self.device)])
+        engs = [self, pipe[0]]
+        streams = pipe[1]
         if max_scat_rows is None:
             max_scat_rows = (batch * min(int(self.inputPar['maxScatt']), 512) + 65536) if self.row_words else 0
         pending = None
@@ -410,8 +418,8 @@ class Engine:
                 yield finish(pending)
             self.next_id = max(self.next_id, first_id + total)
         finally:
-            engs[1].close()
-            self._clones = [c for c in getattr(self, '_clones', []) if c is not engs[1]]
+            for st in streams:
+                st.synchronize()
 
     # ---- unit hooks (parity tests) --------------------------------------------------------------
     def test_sigmas(self, E):
