@@ -39,6 +39,7 @@ struct mcd_ctx {
   DevParams P;
   HostTable tab[MCD_MAX_TABLES];
   bool owns_tables = true;
+  size_t l2_persist_bytes = 0;                // persisting-L2 carve-out (0 = not used)
   float4* sig_poly = nullptr;                 // per-cell quadratics of the cumulative cross-sections
   double sig_poly_err = 0.0;                  // verified max error relative to the total
   int slot_order[MCD_MAX_SHELLS] = {0};
@@ -444,6 +445,12 @@ int mcd_create(const mcd_params* p, const mcd_material* m, int device, mcd_ctx**
   e = cudaGetDeviceProperties(&pr, device);
   if (e != cudaSuccess) { delete c; return fail(nullptr, MCD_ERR_CUDA, "props: %s", cudaGetErrorString(e)); }
   c->sm_count = pr.multiProcessorCount;
+  if (getenv("MCD_L2_PERSIST") && pr.persistingL2CacheMaxSize > 0) {
+    size_t want = (size_t)atoll(getenv("MCD_L2_PERSIST")) << 20;
+    if (want > (size_t)pr.persistingL2CacheMaxSize) want = (size_t)pr.persistingL2CacheMaxSize;
+    if (want && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) c->l2_persist_bytes = want;
+    cudaGetLastError();
+  }
   build_dev_params(c);
   c->P.use_sig_poly = 0;
   if (p->mode == MCD_MODE_DS && c->P.order_static && !getenv("MCD_NO_SIGPOLY"))
@@ -487,6 +494,7 @@ int mcd_clone(const mcd_ctx* parent, mcd_ctx** out) {
   for (int s = 0; s < MCD_MAX_TABLES; ++s) c->tab[s] = parent->tab[s];
   c->owns_tables = false;
   c->li = parent->li;
+  c->l2_persist_bytes = parent->l2_persist_bytes;
   c->n_blocks = parent->n_blocks;
   if ((e = cudaMalloc(&c->ticket, sizeof(unsigned long long))) != cudaSuccess ||
       (e = cudaMalloc(&c->stats, kStatsWords * 8)) != cudaSuccess ||
@@ -644,6 +652,22 @@ int mcd_run(mcd_ctx* c, uint64_t first_id, uint64_t count, void* stream) {
   O.nev = c->nev;
   O.ticket = c->ticket;
   O.stats = c->stats;
+  if (c->par.mode == MCD_MODE_DS && c->l2_persist_bytes > 0 && s != nullptr) {
+    // keep the Moller guide (the first, L2-sized stage of two thirds of the table searches) resident in L2 while
+    // the 1 GB of CDF rows streams through it
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof attr);
+    const HostTable& h = c->tab[MCD_TABLE_MOLLER];
+    size_t bytes = (size_t)h.nE * (MCD_GUIDE + 1) * sizeof(uint32_t);
+    if (bytes > c->l2_persist_bytes) bytes = c->l2_persist_bytes;
+    attr.accessPolicyWindow.base_ptr = h.guide;
+    attr.accessPolicyWindow.num_bytes = bytes;
+    attr.accessPolicyWindow.hitRatio = 1.0f;
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr);      // best effort
+    cudaGetLastError();
+  }
   CU(c, cudaEventRecord(c->ev0, s));
   CU(c, mcd_launch_traj(c->P, O, first_id, count, c->sm_count, s, &c->li));
   CU(c, cudaEventRecord(c->ev1, s));

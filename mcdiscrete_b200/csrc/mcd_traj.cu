@@ -336,19 +336,35 @@ __global__ void scan_apply(const unsigned int* __restrict__ nev, unsigned long l
   if (base <= n && n < base + kScanItems) offsets[n] = run - 0;       // offsets[n] = total (set by the owner of n)
 }
 
-// every stored row of the chunk pool goes to sorted[offsets[rel_id] + event]
-__global__ void scatter_rows(const uint32_t* __restrict__ pool, const unsigned int* __restrict__ chunk_count,
-                             unsigned int nchunks, int row_words, const unsigned long long* __restrict__ offsets,
-                             uint32_t* __restrict__ sorted) {
+// every stored row of the chunk pool goes to sorted[offsets[rel_id] + event].  One block per chunk (1024 rows), one
+// row per thread and pass; rows are moved as 8-byte words when the row length allows (row starts are then 8-byte
+// aligned in both buffers), so a 24-byte row is three loads and three stores.
+__global__ void __launch_bounds__(256) scatter_rows(const uint32_t* __restrict__ pool,
+                                                    const unsigned int* __restrict__ chunk_count, unsigned int nchunks,
+                                                    int row_words, const unsigned long long* __restrict__ offsets,
+                                                    uint32_t* __restrict__ sorted) {
   for (unsigned int c = blockIdx.x; c < nchunks; c += gridDim.x) {
     const unsigned int cnt = chunk_count[c];
-    for (unsigned int r = threadIdx.x; r < cnt; r += blockDim.x) {
-      const uint32_t* src = pool + ((size_t)c * MCD_CHUNK_ROWS + r) * (size_t)row_words;
-      const uint32_t rel = src[0], w1 = src[1];
-      uint32_t* dst = sorted + (offsets[rel] + (unsigned long long)(w1 & 0xffffffu)) * (unsigned long long)row_words;
-      dst[0] = rel;
-      dst[1] = w1;
-      for (int w = 2; w < row_words; ++w) dst[w] = src[w];
+    const uint32_t* cbase = pool + (size_t)c * MCD_CHUNK_ROWS * (size_t)row_words;
+    if ((row_words & 1) == 0) {
+      const int rw2 = row_words >> 1;
+      for (unsigned int r = threadIdx.x; r < cnt; r += blockDim.x) {
+        const uint2* src = reinterpret_cast<const uint2*>(cbase) + (size_t)r * rw2;
+        const uint2 head = __ldcs(src);
+        const unsigned long long d = offsets[head.x] + (unsigned long long)(head.y & 0xffffffu);
+        uint2* dst = reinterpret_cast<uint2*>(sorted) + d * (unsigned long long)rw2;
+        dst[0] = head;
+        for (int w = 1; w < rw2; ++w) dst[w] = __ldcs(src + w);
+      }
+    } else {
+      for (unsigned int r = threadIdx.x; r < cnt; r += blockDim.x) {
+        const uint32_t* src = cbase + (size_t)r * row_words;
+        const uint32_t rel = src[0], w1 = src[1];
+        uint32_t* dst = sorted + (offsets[rel] + (unsigned long long)(w1 & 0xffffffu)) * (unsigned long long)row_words;
+        dst[0] = rel;
+        dst[1] = w1;
+        for (int w = 2; w < row_words; ++w) dst[w] = src[w];
+      }
     }
   }
 }
@@ -364,7 +380,10 @@ cudaError_t mcd_launch_order_scats(const unsigned int* nev, unsigned long long c
   scan_tile_sums<<<ntiles, kScanT, 0, stream>>>(nev, count, tile_tmp);
   scan_tiles<<<1, 1024, 0, stream>>>(tile_tmp, ntiles, total_dev);
   scan_apply<<<ntiles, kScanT, 0, stream>>>(nev, count, tile_tmp, offsets);
-  if (sorted && nchunks) scatter_rows<<<sm_count * 8, 256, 0, stream>>>(pool, chunk_count, nchunks, row_words, offsets, sorted);
+  if (sorted && nchunks) {
+    const unsigned int grid = nchunks < (unsigned int)(sm_count * 64) ? nchunks : (unsigned int)(sm_count * 64);
+    scatter_rows<<<grid, 256, 0, stream>>>(pool, chunk_count, nchunks, row_words, offsets, sorted);
+  }
   return cudaGetLastError();
 }
 
