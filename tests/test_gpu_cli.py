@@ -111,3 +111,46 @@ def test_error_behaviour_and_legacy_wrappers():
     import pickle
     els = pickle.loads(q['electrons'].get())
     assert len(els['outcome']) == 5 and len(pickle.loads(q['scatterings'].get())['energy']) > 5
+
+
+def test_raw_ctypes_sequence_of_INTEGRATION_md():
+    """The bare C-ABI call sequence documented in INTEGRATION.md section 2 (no Engine wrapper)."""
+    import ctypes as C
+    from mcdiscrete_b200 import _lib, material
+    from mcdiscrete_b200.probTables import probTable
+    lib = C.CDLL(_lib.LIB_PATH)
+    lib.mcd_last_error.restype = C.c_char_p
+
+    def check(rc, ctx=None):
+        assert rc == 0, lib.mcd_last_error(ctx).decode()
+    inputPar = dict(E0=20000., Emin=15000., s_tilt=70., thickness=3e6, Wc=10., maxScatt=1000, num_el=5000, material='Si')
+    mat = material(inputPar['material'])
+    m = _lib.Material(mat.params['Z'], len(mat.params['name_s']), mat.params['n_val'], mat.params['E_val'],
+                      mat.atnd, mat.fermi_e, mat.plasmon_e, mat.params['bethe_k'])
+    for i, s in enumerate(mat.params['name_s']):
+        m.shell_E[i], m.shell_n[i] = mat.params['Es'][s], mat.params['ns'][s]
+    p = _lib.Params(E0=inputPar['E0'], Emin=inputPar['Emin'], s_tilt_deg=inputPar['s_tilt'], thickness=inputPar['thickness'],
+                    Wc=inputPar['Wc'], maxScatt=inputPar['maxScatt'], mode=0, el_mask=0xF, scat_mask=0x83, flags=1, seed=12345)
+    ctx = C.c_void_p()
+    check(lib.mcd_create(C.byref(p), C.byref(m), 0, C.byref(ctx)))
+    T = probTable('Moller', mat.params['name_val'], (inputPar['Emin'], inputPar['E0']), 1e-2, 1e-3, mat, Wc=inputPar['Wc'])
+    T.set_Ws(); T.set_Es()
+    G = probTable('Gryzinski', mat.params['name_s'][-1], (inputPar['Emin'], inputPar['E0']), 1e-2, 1e-3, mat)
+    G.set_Ws(); G.set_Es()
+    f = lambda a: np.ascontiguousarray(a, np.float32).ctypes.data_as(C.POINTER(C.c_float))
+    check(lib.mcd_table_build(ctx, 0, f(T.Es), C.c_uint32(len(T.Es)), f(T.Ws), C.c_uint32(len(T.Ws)), C.c_double(0), C.c_double(0), None), ctx)
+    check(lib.mcd_table_build(ctx, 1, f(G.Es), C.c_uint32(len(G.Es)), f(G.Ws), C.c_uint32(len(G.Ws)), C.c_double(G.Wmin),
+                              C.c_double(G.numEl), None), ctx)
+    n = inputPar['num_el']
+    check(lib.mcd_set_capacity(ctx, C.c_uint64(n), C.c_uint64(n * 512)), ctx)
+    check(lib.mcd_run(ctx, C.c_uint64(0), C.c_uint64(n), None), ctx)
+    check(lib.mcd_sync(ctx, None), ctx)
+    els = np.empty(n, dtype=_lib.EL_ROW_DTYPE)
+    check(lib.mcd_drain_els(ctx, els.ctypes.data_as(C.c_void_p), C.c_uint64(0), C.c_uint64(n), None), ctx)
+    check(lib.mcd_sync(ctx, None), ctx)
+    outcome = np.array(['abs', 'bks', 'trsm', 'trdf', 'long'])[els['code'] & 0xff]
+    assert set(outcome) <= {'abs', 'bks'} and 0.3 < (outcome == 'bks').mean() < 0.7
+    n_els, n_sc = C.c_uint64(), C.c_uint64()
+    check(lib.mcd_row_counts(ctx, C.byref(n_els), C.byref(n_sc)), ctx)
+    assert n_els.value == n and n_sc.value > n
+    lib.mcd_destroy(ctx)
