@@ -350,7 +350,7 @@ int alloc_table(mcd_ctx* c, int slot, const float* Es, uint32_t nE, const float*
   // (probTables.py:137-142, 364-379)?  Then the device regenerates grid values instead of loading them.
   d.es_analytic = 0;
   const double starts[2] = {c->par.Emin, es_start_hint};
-  for (int k = 0; k < 2 && !d.es_analytic; ++k) {
+  for (int k = 0; k < 2 && !d.es_analytic && !getenv("MCD_NO_ANALYTIC_ES"); ++k) {
     const double start = starts[k], stop = c->par.E0;
     if (!(start > 0) || !(stop > start)) continue;
     const double step = (stop - start) / (double)(nE - 1);

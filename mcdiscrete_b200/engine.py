@@ -342,6 +342,13 @@ class Engine:
         (default: continue after the previous run) and return a RunResult."""
         count = int(count if count is not None else self.inputPar['num_el'])
         first_id = int(self.next_id if first_id is None else first_id)
+        if count <= 0:                                 # nothing to do (the reference spawns no job for num_el = 0)
+            empty = np.empty(0, _lib.EL_ROW_DTYPE)
+            zero = {k: 0 for k in ('electrons_done', 'events', 'double_records', 'scat_rows_stored',
+                                   'scat_rows_dropped', 'nan_clamped', 'select_exact')}
+            zero['outcome'] = {n: 0 for n in _lib.OUTCOMES}
+            zero['channel'] = [0] * (self.cmat.n_shells + 3)
+            return RunResult(first_id, 0, empty, {}, zero, 0.0)
         if self.params.mode == _lib.MODE_DS and self.tables is None:
             from .probTables import genTables
             genTables(self.inputPar, engine=self)

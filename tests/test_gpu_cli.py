@@ -154,3 +154,35 @@ def test_raw_ctypes_sequence_of_INTEGRATION_md():
     check(lib.mcd_row_counts(ctx, C.byref(n_els), C.byref(n_sc)), ctx)
     assert n_els.value == n and n_sc.value > n
     lib.mcd_destroy(ctx)
+
+
+def test_edge_cases_empty_and_degenerate_runs():
+    from mcdiscrete_b200 import material, genTables, multiTraj_DS
+    from mcdiscrete_b200.engine import Engine
+    ip = dict(num_el=0, E0=20000., Emin=15000., material='Si', s_tilt=70., thickness=3e6, elastic='Ruth_vanilla',
+              mode='DS', Bethe_model='classical', diffMFP=False, gen_tables=True, tol_E=1e-2, tol_W=1e-3,
+              maxScatt=1000, Wc=10., electron_output=['outcome', 'final_E', 'final_dir', 'last_pos'],
+              scatter_output=['type', 'energy'])
+    what = {'el_output': ip['electron_output'], 'scat_output': ip['scatter_output']}
+    tables = genTables(ip)
+    assert multiTraj_DS(ip, 0, material('Si'), tables, what) == []           # no electrons: no rows, no error
+    eng = Engine(dict(ip, maxScatt=0), device=0)                             # every electron is 'long' at once
+    genTables(ip, engine=eng)
+    r = eng.run(count=1000, first_id=0)
+    assert (r.outcome == 4).all() and r.counters['events'] == 0 and len(r.scats) == 0
+    assert (r.els['final_E'] == 20000.).all() and (r.els['last_z'] == 0).all()
+    eng.close()
+    eng = Engine(dict(ip, maxScatt=1), device=0)                             # exactly one event each
+    genTables(ip, engine=eng)
+    r = eng.run(count=1000, first_id=0, ordered=True)
+    assert r.counters['events'] == 1000 and len(r.scats) == 1000
+    assert np.array_equal(r.scats['el'], np.arange(1000)) and (r.scats['ev'] == 0).all()
+    assert set(np.unique(r.outcome)) <= {0, 1, 4}
+    eng.close()
+    # one electron, very large id (64-bit Philox counter)
+    eng = Engine(ip, device=0)
+    genTables(ip, engine=eng)
+    a = eng.run(count=1, first_id=2 ** 45 + 12345)
+    b = eng.run(count=3, first_id=2 ** 45 + 12344)
+    assert a.els[0] == b.els[1]
+    eng.close()
