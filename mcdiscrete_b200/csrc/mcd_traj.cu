@@ -116,23 +116,53 @@ traj_kernel(const __grid_constant__ DevParams P, const DevOut O, const unsigned 
     const bool has_row = alive && (ev < (uint32_t)P.maxScatt);
     int outcome = (alive && !has_row) ? MCD_OUT_LONG : -1;
     EventRow row;
-    OutcomeSnap sn;
     row.flags = 0;
     row.slot = 0;
+    row.E = e.E;
     if (has_row) {
       const float4 u = event_uniforms(P, first_id + rel_id, ev);
       if (MODE == MCD_MODE_DS) {
         EventMid mid;
-        ds_phase_a<S>(P, e, u, row, sn, mid);
-        ds_phase_b(P, e, u, row, sn, mid);
+        ds_phase_a<S>(P, e, u, row, mid);
+        ds_phase_b(P, e, u, row, mid);
       } else {
-        cont_event(P, e, u, row, sn);
+        cont_event(P, e, u, row);
       }
       outcome = row.outcome;
       ++my_events;
-    } else if (outcome == MCD_OUT_LONG) {
-      snap(sn, e);
     }
+
+    // ---- retire: saveOutcomes row (electron.py:105-113), histograms, counters.  Taken BEFORE the rotation of this
+    // event: final_E = energy before the event's loss, final_dir = direction before its rotation, last_pos =
+    // position as update_xyz left it -----------------------------------------------------------------
+    if (outcome >= 0) {
+      const bool dbl = (row.flags & MCD_EVF_DOUBLE) != 0;
+      if (want_scats) O.nev[rel_id] = ev + (has_row ? 1u : 0u);
+      float4* dst = reinterpret_cast<float4*>(O.els + rel_id);
+      dst[0] = make_float4(__uint_as_float((uint32_t)outcome | (dbl ? 0x100u : 0u)), row.E, e.dx, e.dy);
+      dst[1] = make_float4(e.dz, e.x, e.y, e.z);
+      atomicAdd(&s_cnt[kCntOutcome + outcome], 1ull);
+      atomicAdd(&s_cnt[kCntDone], 1ull);
+      atomicAdd(&s_cnt[kCntEvents], (unsigned long long)my_events);
+      if (dbl) atomicAdd(&s_cnt[kCntDouble], 1ull);
+      my_events = 0u;
+      if (want_hist && outcome == MCD_OUT_BKS) {
+        int b = (int)((row.E - P.hist.e_lo) * P.hist.e_scale);
+        b = max(0, min(b, MCD_HIST_E_BINS - 1));
+        atomicAdd(&s_hist[b], 1u);
+        const float pol = acosf(fminf(1.0f, fmaxf(-1.0f, -e.dz))) * 57.29577951308232f;       // from -z normal
+        b = max(0, min((int)(pol * 2.0f), MCD_HIST_POLAR_BINS - 1));
+        atomicAdd(&s_hist[MCD_HIST_E_BINS + b], 1u);
+        const float az = atan2f(e.dy, e.dx) * 57.29577951308232f + 180.0f;
+        b = max(0, min((int)az, MCD_HIST_AZ_BINS - 1));
+        atomicAdd(&s_hist[MCD_HIST_E_BINS + MCD_HIST_POLAR_BINS + b], 1u);
+        b = max(0, min((int)(e.z * P.hist.depth_scale), MCD_HIST_DEPTH_BINS - 1));
+        atomicAdd(&s_hist[MCD_HIST_E_BINS + MCD_HIST_POLAR_BINS + MCD_HIST_AZ_BINS + b], 1u);
+      }
+      alive = false;
+    }
+    // update_direction of this event (the exit event still rotates and, if requested, records its direction)
+    if (has_row) event_rotate(e, row);
 
     // ---- scats append: warp-local slots in the warp's chunk; a new chunk when it is full --------
     if (want_scats) {
@@ -175,33 +205,6 @@ traj_kernel(const __grid_constant__ DevParams P, const DevOut O, const unsigned 
       ++ev;
     }
 
-    // ---- retire: saveOutcomes row (electron.py:105-113), histograms, counters -------------------
-    if (outcome >= 0) {
-      const bool dbl = (row.flags & MCD_EVF_DOUBLE) != 0;
-      if (want_scats) O.nev[rel_id] = ev;
-      float4* dst = reinterpret_cast<float4*>(O.els + rel_id);
-      dst[0] = make_float4(__uint_as_float((uint32_t)outcome | (dbl ? 0x100u : 0u)), sn.E, sn.dx, sn.dy);
-      dst[1] = make_float4(sn.dz, sn.x, sn.y, sn.z);
-      atomicAdd(&s_cnt[kCntOutcome + outcome], 1ull);
-      atomicAdd(&s_cnt[kCntDone], 1ull);
-      atomicAdd(&s_cnt[kCntEvents], (unsigned long long)my_events);
-      if (dbl) atomicAdd(&s_cnt[kCntDouble], 1ull);
-      my_events = 0u;
-      if (want_hist && outcome == MCD_OUT_BKS) {
-        int b = (int)((sn.E - P.hist.e_lo) * P.hist.e_scale);
-        b = max(0, min(b, MCD_HIST_E_BINS - 1));
-        atomicAdd(&s_hist[b], 1u);
-        const float pol = acosf(fminf(1.0f, fmaxf(-1.0f, -sn.dz))) * 57.29577951308232f;      // from -z normal
-        b = max(0, min((int)(pol * 2.0f), MCD_HIST_POLAR_BINS - 1));
-        atomicAdd(&s_hist[MCD_HIST_E_BINS + b], 1u);
-        const float az = atan2f(sn.dy, sn.dx) * 57.29577951308232f + 180.0f;
-        b = max(0, min((int)az, MCD_HIST_AZ_BINS - 1));
-        atomicAdd(&s_hist[MCD_HIST_E_BINS + MCD_HIST_POLAR_BINS + b], 1u);
-        b = max(0, min((int)(sn.z * P.hist.depth_scale), MCD_HIST_DEPTH_BINS - 1));
-        atomicAdd(&s_hist[MCD_HIST_E_BINS + MCD_HIST_POLAR_BINS + MCD_HIST_AZ_BINS + b], 1u);
-      }
-      alive = false;
-    }
   }
 
   // ---- close this warp's chunk, flush block statistics ---------------------------------------------

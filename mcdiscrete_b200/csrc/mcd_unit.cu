@@ -155,15 +155,16 @@ __global__ void k_lookup(const __grid_constant__ DevParams P, int slot, const fl
 }
 
 template <int S>
-__device__ void step_one(const DevParams& P, bool on, ElState& e, float4 u, EventRow& row, OutcomeSnap& sn) {
+__device__ void step_one(const DevParams& P, bool on, ElState& e, float4 u, EventRow& row) {
   if (!on) return;
   if (P.mode == MCD_MODE_DS) {
     EventMid mid;
-    ds_phase_a<S>(P, e, u, row, sn, mid);
-    ds_phase_b(P, e, u, row, sn, mid);
+    ds_phase_a<S>(P, e, u, row, mid);
+    ds_phase_b(P, e, u, row, mid);
   } else {
-    cont_event(P, e, u, row, sn);
+    cont_event(P, e, u, row);
   }
+  event_rotate(e, row);
 }
 
 __global__ void k_step(const __grid_constant__ DevParams P, const float* st, const float* uu, uint64_t n,
@@ -180,16 +181,15 @@ __global__ void k_step(const __grid_constant__ DevParams P, const float* st, con
     u = make_float4(uu[4 * i], uu[4 * i + 1], uu[4 * i + 2], uu[4 * i + 3]);
   }
   EventRow row;
-  OutcomeSnap sn;
   switch (P.m.nshell) {
-    case 1: step_one<1>(P, on, e, u, row, sn); break;
-    case 2: step_one<2>(P, on, e, u, row, sn); break;
-    case 3: step_one<3>(P, on, e, u, row, sn); break;
-    case 4: step_one<4>(P, on, e, u, row, sn); break;
-    case 5: step_one<5>(P, on, e, u, row, sn); break;
-    case 6: step_one<6>(P, on, e, u, row, sn); break;
-    case 7: step_one<7>(P, on, e, u, row, sn); break;
-    default: step_one<8>(P, on, e, u, row, sn); break;
+    case 1: step_one<1>(P, on, e, u, row); break;
+    case 2: step_one<2>(P, on, e, u, row); break;
+    case 3: step_one<3>(P, on, e, u, row); break;
+    case 4: step_one<4>(P, on, e, u, row); break;
+    case 5: step_one<5>(P, on, e, u, row); break;
+    case 6: step_one<6>(P, on, e, u, row); break;
+    case 7: step_one<7>(P, on, e, u, row); break;
+    default: step_one<8>(P, on, e, u, row); break;
   }
   if (!on) return;
   float* o = st_out + 10 * i;
