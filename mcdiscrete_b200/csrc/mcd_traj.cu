@@ -59,7 +59,7 @@ __device__ __forceinline__ void store_scat_row(uint32_t* __restrict__ dst, uint3
   }
 }
 
-template <int S, int MODE>
+template <int S, int MODE, bool SCATS>
 __global__ void __launch_bounds__(kThreads, MCD_MIN_BLOCKS)
 traj_kernel(const __grid_constant__ DevParams P, const DevOut O, const unsigned long long first_id,
             const unsigned long long count) {
@@ -74,7 +74,7 @@ traj_kernel(const __grid_constant__ DevParams P, const DevOut O, const unsigned 
 
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lt = lanemask_lt();
-  const bool want_scats = (P.scat_row_words > 0) && (O.scats != nullptr);
+  constexpr bool want_scats = SCATS;            // compile time: the no-scats kernel carries no row fields
   const bool want_hist = (P.flags & MCD_FLAG_HISTOGRAMS) != 0u;
   const bool want_chan = (P.flags & MCD_FLAG_CHANNEL_COUNTS) != 0u;
   int chunk = -1;                                // this warp's current chunk (warp-uniform)
@@ -239,19 +239,24 @@ traj_kernel(const __grid_constant__ DevParams P, const DevOut O, const unsigned 
 
 typedef void (*TrajKernel)(const DevParams, const DevOut, const unsigned long long, const unsigned long long);
 
-TrajKernel pick_kernel(const DevParams& P) {
-  if (P.mode == MCD_MODE_CONT) return traj_kernel<1, MCD_MODE_CONT>;
+template <bool SCATS>
+TrajKernel pick_kernel_t(const DevParams& P) {
+  if (P.mode == MCD_MODE_CONT) return traj_kernel<1, MCD_MODE_CONT, SCATS>;
   switch (P.m.nshell) {
-    case 1: return traj_kernel<1, MCD_MODE_DS>;
-    case 2: return traj_kernel<2, MCD_MODE_DS>;
-    case 3: return traj_kernel<3, MCD_MODE_DS>;
-    case 4: return traj_kernel<4, MCD_MODE_DS>;
-    case 5: return traj_kernel<5, MCD_MODE_DS>;
-    case 6: return traj_kernel<6, MCD_MODE_DS>;
-    case 7: return traj_kernel<7, MCD_MODE_DS>;
-    case 8: return traj_kernel<8, MCD_MODE_DS>;
+    case 1: return traj_kernel<1, MCD_MODE_DS, SCATS>;
+    case 2: return traj_kernel<2, MCD_MODE_DS, SCATS>;
+    case 3: return traj_kernel<3, MCD_MODE_DS, SCATS>;
+    case 4: return traj_kernel<4, MCD_MODE_DS, SCATS>;
+    case 5: return traj_kernel<5, MCD_MODE_DS, SCATS>;
+    case 6: return traj_kernel<6, MCD_MODE_DS, SCATS>;
+    case 7: return traj_kernel<7, MCD_MODE_DS, SCATS>;
+    case 8: return traj_kernel<8, MCD_MODE_DS, SCATS>;
     default: return nullptr;
   }
+}
+
+TrajKernel pick_kernel(const DevParams& P, bool scats) {
+  return scats ? pick_kernel_t<true>(P) : pick_kernel_t<false>(P);
 }
 
 }  // namespace
@@ -396,7 +401,8 @@ unsigned long long mcd_order_tiles(unsigned long long count) {
 }
 
 cudaError_t mcd_traj_max_blocks(const DevParams& P, int sm_count, TrajLaunchInfo* info) {
-  TrajKernel k = pick_kernel(P);
+  // both variants have the same launch bounds; the occupancy of the row-writing one is reported
+  TrajKernel k = pick_kernel(P, true);
   if (!k) return cudaErrorInvalidValue;
   int per_sm = 0;
   cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kThreads, 0);
@@ -418,7 +424,7 @@ cudaError_t mcd_traj_max_blocks(const DevParams& P, int sm_count, TrajLaunchInfo
 
 cudaError_t mcd_launch_traj(const DevParams& P, const DevOut& O, unsigned long long first_id,
                             unsigned long long count, int sm_count, cudaStream_t stream, TrajLaunchInfo* info) {
-  TrajKernel k = pick_kernel(P);
+  TrajKernel k = pick_kernel(P, (P.scat_row_words > 0) && (O.scats != nullptr));
   if (!k) return cudaErrorInvalidValue;
   TrajLaunchInfo li;
   cudaError_t err = mcd_traj_max_blocks(P, sm_count, &li);
