@@ -83,9 +83,8 @@ traj_kernel(const __grid_constant__ DevParams P, const DevOut O, const unsigned 
 
   bool alive = false, exhausted = false;
   ElState e;
-  unsigned long long rel_id = 0ull;
-  uint32_t ev = 0u;
-  unsigned int my_events = 0u;
+  uint32_t rel_id = 0u;                          // id relative to first_id (a run holds < 2^32 electrons)
+  uint32_t ev = 0u;                              // events executed by the current electron
 
   while (true) {
     // ---- refill dead lanes (multiScatter.py:105-107: a fresh electron at pos0 / dir0) ----------
@@ -96,8 +95,9 @@ traj_kernel(const __grid_constant__ DevParams P, const DevOut O, const unsigned 
       if ((int)lane == leader) base = atomicAdd(O.ticket, (unsigned long long)__popc(need));
       base = __shfl_sync(MCD_FULL_MASK, base, leader);
       if (!alive && !exhausted) {
-        rel_id = base + (unsigned long long)__popc(need & lt);
-        if (rel_id < count) {
+        const unsigned long long rid = base + (unsigned long long)__popc(need & lt);
+        rel_id = (uint32_t)rid;
+        if (rid < count) {
           alive = true;
           ev = 0u;
           e.E = P.E0;
@@ -129,7 +129,6 @@ traj_kernel(const __grid_constant__ DevParams P, const DevOut O, const unsigned 
         cont_event(P, e, u, row);
       }
       outcome = row.outcome;
-      ++my_events;
     }
 
     // ---- retire: saveOutcomes row (electron.py:105-113), histograms, counters.  Taken BEFORE the rotation of this
@@ -137,15 +136,15 @@ traj_kernel(const __grid_constant__ DevParams P, const DevOut O, const unsigned 
     // position as update_xyz left it -----------------------------------------------------------------
     if (outcome >= 0) {
       const bool dbl = (row.flags & MCD_EVF_DOUBLE) != 0;
-      if (want_scats) O.nev[rel_id] = ev + (has_row ? 1u : 0u);
+      const uint32_t nev = ev + (has_row ? 1u : 0u);
+      if (want_scats) O.nev[rel_id] = nev;
       float4* dst = reinterpret_cast<float4*>(O.els + rel_id);
       dst[0] = make_float4(__uint_as_float((uint32_t)outcome | (dbl ? 0x100u : 0u)), row.E, e.dx, e.dy);
       dst[1] = make_float4(e.dz, e.x, e.y, e.z);
       atomicAdd(&s_cnt[kCntOutcome + outcome], 1ull);
       atomicAdd(&s_cnt[kCntDone], 1ull);
-      atomicAdd(&s_cnt[kCntEvents], (unsigned long long)my_events);
+      atomicAdd(&s_cnt[kCntEvents], (unsigned long long)nev);
       if (dbl) atomicAdd(&s_cnt[kCntDouble], 1ull);
-      my_events = 0u;
       if (want_hist && outcome == MCD_OUT_BKS) {
         int b = (int)((row.E - P.hist.e_lo) * P.hist.e_scale);
         b = max(0, min(b, MCD_HIST_E_BINS - 1));
