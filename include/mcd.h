@@ -210,6 +210,9 @@ int mcd_hist_ranges(const mcd_ctx* ctx, double* e_lo, double* e_hi, double* dept
 int mcd_last_kernel_ms(mcd_ctx* ctx, float* ms);
 /* Launch geometry of the trajectory kernel (blocks, threads, registers/thread, blocks/SM). */
 int mcd_launch_info(mcd_ctx* ctx, int* blocks, int* threads, int* regs, int* blocks_per_sm);
+/* Kernel launches the last mcd_run made: 1, or the passes of the tail hand-over (statistics-only DS runs: warps
+ * that are down to a few electrons pass them to a follow-up launch that runs them in full warps). */
+int mcd_last_launches(mcd_ctx* ctx, int* launches);
 
 /* ---- roofline denominators ---------------------------------------------------------------------- */
 /* Measure the FP32 FMA peak (TFLOP/s, FMA = 2 flop) and the MUFU/XU peak (1e12 transcendental op/s) of

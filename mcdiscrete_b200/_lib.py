@@ -91,6 +91,7 @@ SYMBOLS = {
     'mcd_hist_ranges': (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     'mcd_last_kernel_ms': (C.c_int, [_P, C.POINTER(C.c_float)]),
     'mcd_launch_info': (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    'mcd_last_launches': (C.c_int, [_P, C.POINTER(C.c_int)]),
     'mcd_measure_peaks': (C.c_int, [C.c_int, _F, _F, _F]),
     'mcd_test_sigmas': (C.c_int, [_P, _F, _U64, _F, _F]),
     'mcd_test_cum': (C.c_int, [_P, _F, _U64, _F, _I, _I, C.POINTER(C.c_double)]),

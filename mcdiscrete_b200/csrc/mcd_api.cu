@@ -57,7 +57,9 @@ struct mcd_ctx {
   unsigned long long* tile_tmp = nullptr;
   unsigned long long* total_dev = nullptr;
   bool ordered = false;
-  unsigned long long* ticket = nullptr;
+  unsigned long long* ticket = nullptr;       // 8 words: [0..3] id tickets of the passes, [4..6] leftover counts
+  uint32_t* rq[2] = {nullptr, nullptr};       // leftover queues of the tail hand-over (statistics-only DS runs)
+  unsigned int rq_cap = 0;
   unsigned long long* stats = nullptr;
   int n_blocks = 0;
   TrajLaunchInfo li{};
@@ -417,6 +419,17 @@ int mcd_device_info(int device, char* name, int name_len, int* sm_count, int* cc
   return MCD_OK;
 }
 
+// leftover queues of the tail hand-over: a warp hands over at most 32 electrons, 12 words each
+static cudaError_t alloc_queues(mcd_ctx* c) {
+  if (!mcd_traj_uses_queue(c->P, c->P.scat_row_words > 0)) return cudaSuccess;
+  c->rq_cap = (unsigned int)(c->li.blocks * c->li.threads);
+  for (int i = 0; i < 2; ++i) {
+    cudaError_t e = cudaMalloc(&c->rq[i], (size_t)c->rq_cap * 12 * sizeof(uint32_t));
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
 int mcd_create(const mcd_params* p, const mcd_material* m, int device, mcd_ctx** out) {
   if (!p || !m || !out) return fail(nullptr, MCD_ERR_INVALID, "null argument");
   *out = nullptr;
@@ -458,7 +471,7 @@ int mcd_create(const mcd_params* p, const mcd_material* m, int device, mcd_ctx**
   mcd_scat_layout L;
   layout_of(p->scat_mask, &L);
   c->P.scat_row_words = (int)L.row_words;
-  e = mcd_traj_max_blocks(c->P, c->sm_count, &c->li);
+  e = mcd_traj_max_blocks(c->P, c->P.scat_row_words > 0, c->sm_count, &c->li);
   if (e != cudaSuccess) {
     std::string msg = cudaGetErrorString(e);
     delete c;
@@ -466,7 +479,7 @@ int mcd_create(const mcd_params* p, const mcd_material* m, int device, mcd_ctx**
                 "sm_100a only and has no fallback", device, pr.name, msg.c_str());
   }
   c->n_blocks = c->li.blocks;
-  if ((e = cudaMalloc(&c->ticket, sizeof(unsigned long long))) != cudaSuccess ||
+  if ((e = cudaMalloc(&c->ticket, 8 * sizeof(unsigned long long))) != cudaSuccess || (e = alloc_queues(c)) != cudaSuccess ||
       (e = cudaMalloc(&c->stats, kStatsWords * 8)) != cudaSuccess ||
       (e = cudaMalloc(&c->chunk_next, sizeof(unsigned int))) != cudaSuccess ||
       (e = cudaMemset(c->stats, 0, kStatsWords * 8)) != cudaSuccess ||
@@ -496,7 +509,7 @@ int mcd_clone(const mcd_ctx* parent, mcd_ctx** out) {
   c->li = parent->li;
   c->l2_persist_bytes = parent->l2_persist_bytes;
   c->n_blocks = parent->n_blocks;
-  if ((e = cudaMalloc(&c->ticket, sizeof(unsigned long long))) != cudaSuccess ||
+  if ((e = cudaMalloc(&c->ticket, 8 * sizeof(unsigned long long))) != cudaSuccess || (e = alloc_queues(c)) != cudaSuccess ||
       (e = cudaMalloc(&c->stats, kStatsWords * 8)) != cudaSuccess ||
       (e = cudaMalloc(&c->chunk_next, sizeof(unsigned int))) != cudaSuccess ||
       (e = cudaMemset(c->stats, 0, kStatsWords * 8)) != cudaSuccess ||
@@ -515,6 +528,7 @@ int mcd_destroy(mcd_ctx* c) {
   if (c->owns_tables) for (auto& t : c->tab) free_table(t);
   if (c->owns_tables) cudaFree(c->sig_poly);
   cudaFree(c->els); cudaFree(c->scats); cudaFree(c->chunk_next); cudaFree(c->chunk_count); cudaFree(c->ticket);
+  cudaFree(c->rq[0]); cudaFree(c->rq[1]);
   cudaFree(c->nev); cudaFree(c->sorted); cudaFree(c->offsets); cudaFree(c->tile_tmp); cudaFree(c->total_dev);
   cudaFree(c->stats);
   if (c->ev0) cudaEventDestroy(c->ev0);
@@ -640,10 +654,10 @@ int mcd_run(mcd_ctx* c, uint64_t first_id, uint64_t count, void* stream) {
         if (!c->tab[MCD_TABLE_GRYZ0 + k].cdf) return fail(c, MCD_ERR_STATE, "per-shell mode: Gryzinski table %d missing", k);
   }
   cudaStream_t s = (cudaStream_t)stream;
-  CU(c, cudaMemsetAsync(c->ticket, 0, sizeof(unsigned long long), s));
+  CU(c, cudaMemsetAsync(c->ticket, 0, 8 * sizeof(unsigned long long), s));
   CU(c, cudaMemsetAsync(c->chunk_next, 0, sizeof(unsigned int), s));
   if (c->n_chunks) CU(c, cudaMemsetAsync(c->chunk_count, 0, (size_t)c->n_chunks * sizeof(unsigned int), s));
-  DevOut O;
+  DevOut O{};
   O.els = c->els;
   O.scats = c->scats;
   O.n_chunks = c->n_chunks;
@@ -652,6 +666,11 @@ int mcd_run(mcd_ctx* c, uint64_t first_id, uint64_t count, void* stream) {
   O.nev = c->nev;
   O.ticket = c->ticket;
   O.stats = c->stats;
+  O.rq[0] = c->rq[0];
+  O.rq[1] = c->rq[1];
+  O.rq_counts = c->ticket + 4;
+  O.rq_cap = c->rq_cap;
+  O.dump_T = -1;
   if (c->par.mode == MCD_MODE_DS && c->l2_persist_bytes > 0 && s != nullptr) {
     // keep the Moller guide (the first, L2-sized stage of two thirds of the table searches) resident in L2 while
     // the 1 GB of CDF rows streams through it
@@ -858,6 +877,12 @@ int mcd_launch_info(mcd_ctx* c, int* blocks, int* threads, int* regs, int* block
   if (threads) *threads = c->li.threads;
   if (regs) *regs = c->li.regs;
   if (blocks_per_sm) *blocks_per_sm = c->li.blocks_per_sm;
+  return MCD_OK;
+}
+
+int mcd_last_launches(mcd_ctx* c, int* launches) {
+  if (!c || !launches) return fail(nullptr, MCD_ERR_INVALID, "null argument");
+  *launches = c->li.launches;
   return MCD_OK;
 }
 

@@ -20,12 +20,14 @@ struct TableBuildArgs {
 
 struct TrajLaunchInfo {
   int blocks, threads, regs, blocks_per_sm;
+  int launches;             // kernel launches per mcd_run (tail hand-over passes)
 };
 
 // mcd_traj.cu
 cudaError_t mcd_launch_traj(const DevParams& P, const DevOut& O, unsigned long long first_id,
                             unsigned long long count, int sm_count, cudaStream_t stream, TrajLaunchInfo* info);
-cudaError_t mcd_traj_max_blocks(const DevParams& P, int sm_count, TrajLaunchInfo* info);
+cudaError_t mcd_traj_max_blocks(const DevParams& P, bool scats, int sm_count, TrajLaunchInfo* info);
+int mcd_traj_uses_queue(const DevParams& P, bool scats);     // 1 if mcd_launch_traj wants the leftover queues
 
 cudaError_t mcd_launch_order_scats(const unsigned int* nev, unsigned long long count, unsigned long long* tile_tmp,
                                    unsigned long long* offsets, unsigned long long* total_dev, const uint32_t* pool,

@@ -59,6 +59,61 @@ __device__ __forceinline__ void store_scat_row(uint32_t* __restrict__ dst, uint3
   }
 }
 
+// saveOutcomes (electron.py:105-113) of a lane whose trajectory ended: the 32-byte els row (one full sector, two
+// 16-byte stores), outcome / event counters and, for 'bks', the fused backscatter histograms.  preE = energy before
+// the event's loss; e = direction before the event's rotation, position as update_xyz left it.
+__device__ __forceinline__ void retire_lane(const DevParams& P, const DevOut& O, unsigned int* s_hist,
+                                            unsigned long long* s_cnt, bool want_hist, int outcome, bool dbl,
+                                            float preE, const ElState& e, uint32_t rel_id, uint32_t nev) {
+  float4* dst = reinterpret_cast<float4*>(O.els + rel_id);
+  dst[0] = make_float4(__uint_as_float((uint32_t)outcome | (dbl ? 0x100u : 0u)), preE, e.dx, e.dy);
+  dst[1] = make_float4(e.dz, e.x, e.y, e.z);
+  atomicAdd(&s_cnt[kCntOutcome + outcome], 1ull);
+  atomicAdd(&s_cnt[kCntDone], 1ull);
+  atomicAdd(&s_cnt[kCntEvents], (unsigned long long)nev);
+  if (dbl) atomicAdd(&s_cnt[kCntDouble], 1ull);
+  if (want_hist && outcome == MCD_OUT_BKS) {
+    int b = (int)((preE - P.hist.e_lo) * P.hist.e_scale);
+    b = max(0, min(b, MCD_HIST_E_BINS - 1));
+    atomicAdd(&s_hist[b], 1u);
+    const float pol = acosf(fminf(1.0f, fmaxf(-1.0f, -e.dz))) * 57.29577951308232f;       // from -z normal
+    b = max(0, min((int)(pol * 2.0f), MCD_HIST_POLAR_BINS - 1));
+    atomicAdd(&s_hist[MCD_HIST_E_BINS + b], 1u);
+    const float az = atan2f(e.dy, e.dx) * 57.29577951308232f + 180.0f;
+    b = max(0, min((int)az, MCD_HIST_AZ_BINS - 1));
+    atomicAdd(&s_hist[MCD_HIST_E_BINS + MCD_HIST_POLAR_BINS + b], 1u);
+    b = max(0, min((int)(e.z * P.hist.depth_scale), MCD_HIST_DEPTH_BINS - 1));
+    atomicAdd(&s_hist[MCD_HIST_E_BINS + MCD_HIST_POLAR_BINS + MCD_HIST_AZ_BINS + b], 1u);
+  }
+}
+
+// block statistics -> global stats block (histograms || mcd_counters), once per block
+__device__ __forceinline__ void flush_block_stats(const DevOut& O, const unsigned int* s_hist,
+                                                  const unsigned long long* s_cnt, const unsigned long long* s_rows,
+                                                  bool want_scats, bool want_chan) {
+  for (int i = threadIdx.x; i < MCD_HIST_TOTAL; i += kThreads) {
+    const unsigned int v = s_hist[i];
+    if (v) atomicAdd(O.stats + i, (unsigned long long)v);
+  }
+  unsigned long long* cnt = O.stats + MCD_HIST_TOTAL;
+  // mcd_counters layout: electrons_done, events, outcome[5], double_records, stored, dropped, nan, exact, channel[]
+  if (threadIdx.x == 0) {
+    atomicAdd(cnt + 0, s_cnt[kCntDone]);
+    atomicAdd(cnt + 1, s_cnt[kCntEvents]);
+    for (int i = 0; i < 5; ++i) if (s_cnt[kCntOutcome + i]) atomicAdd(cnt + 2 + i, s_cnt[kCntOutcome + i]);
+    if (s_cnt[kCntDouble]) atomicAdd(cnt + 7, s_cnt[kCntDouble]);
+    if (want_scats) {
+      if (s_rows[0]) atomicAdd(cnt + 8, s_rows[0]);
+      if (s_rows[1]) atomicAdd(cnt + 9, s_rows[1]);
+    }
+    if (s_cnt[kCntNan]) atomicAdd(cnt + 10, s_cnt[kCntNan]);
+    if (s_cnt[kCntExact]) atomicAdd(cnt + 11, s_cnt[kCntExact]);
+    if (want_chan)
+      for (int i = 0; i < MCD_MAX_CHANNELS; ++i)
+        if (s_cnt[kCntChan + i]) atomicAdd(cnt + 12 + i, s_cnt[kCntChan + i]);
+  }
+}
+
 template <int S, int MODE, bool SCATS>
 __global__ void __launch_bounds__(kThreads, MCD_MIN_BLOCKS)
 traj_kernel(const __grid_constant__ DevParams P, const DevOut O, const unsigned long long first_id,
@@ -135,29 +190,9 @@ traj_kernel(const __grid_constant__ DevParams P, const DevOut O, const unsigned 
     // event: final_E = energy before the event's loss, final_dir = direction before its rotation, last_pos =
     // position as update_xyz left it -----------------------------------------------------------------
     if (outcome >= 0) {
-      const bool dbl = (row.flags & MCD_EVF_DOUBLE) != 0;
       const uint32_t nev = ev + (has_row ? 1u : 0u);
       if (want_scats) O.nev[rel_id] = nev;
-      float4* dst = reinterpret_cast<float4*>(O.els + rel_id);
-      dst[0] = make_float4(__uint_as_float((uint32_t)outcome | (dbl ? 0x100u : 0u)), row.E, e.dx, e.dy);
-      dst[1] = make_float4(e.dz, e.x, e.y, e.z);
-      atomicAdd(&s_cnt[kCntOutcome + outcome], 1ull);
-      atomicAdd(&s_cnt[kCntDone], 1ull);
-      atomicAdd(&s_cnt[kCntEvents], (unsigned long long)nev);
-      if (dbl) atomicAdd(&s_cnt[kCntDouble], 1ull);
-      if (want_hist && outcome == MCD_OUT_BKS) {
-        int b = (int)((row.E - P.hist.e_lo) * P.hist.e_scale);
-        b = max(0, min(b, MCD_HIST_E_BINS - 1));
-        atomicAdd(&s_hist[b], 1u);
-        const float pol = acosf(fminf(1.0f, fmaxf(-1.0f, -e.dz))) * 57.29577951308232f;       // from -z normal
-        b = max(0, min((int)(pol * 2.0f), MCD_HIST_POLAR_BINS - 1));
-        atomicAdd(&s_hist[MCD_HIST_E_BINS + b], 1u);
-        const float az = atan2f(e.dy, e.dx) * 57.29577951308232f + 180.0f;
-        b = max(0, min((int)az, MCD_HIST_AZ_BINS - 1));
-        atomicAdd(&s_hist[MCD_HIST_E_BINS + MCD_HIST_POLAR_BINS + b], 1u);
-        b = max(0, min((int)(e.z * P.hist.depth_scale), MCD_HIST_DEPTH_BINS - 1));
-        atomicAdd(&s_hist[MCD_HIST_E_BINS + MCD_HIST_POLAR_BINS + MCD_HIST_AZ_BINS + b], 1u);
-      }
+      retire_lane(P, O, s_hist, s_cnt, want_hist, outcome, (row.flags & MCD_EVF_DOUBLE) != 0, row.E, e, rel_id, nev);
       alive = false;
     }
     // update_direction of this event (the exit event still rotates and, if requested, records its direction)
@@ -213,27 +248,247 @@ traj_kernel(const __grid_constant__ DevParams P, const DevOut O, const unsigned 
     if (w_dropped) atomicAdd(&s_rows[1], (unsigned long long)w_dropped);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < MCD_HIST_TOTAL; i += kThreads) {
-    const unsigned int v = s_hist[i];
-    if (v) atomicAdd(O.stats + i, (unsigned long long)v);
-  }
-  unsigned long long* cnt = O.stats + MCD_HIST_TOTAL;
-  // mcd_counters layout: electrons_done, events, outcome[5], double_records, stored, dropped, nan, exact, channel[]
-  if (threadIdx.x == 0) {
-    atomicAdd(cnt + 0, s_cnt[kCntDone]);
-    atomicAdd(cnt + 1, s_cnt[kCntEvents]);
-    for (int i = 0; i < 5; ++i) if (s_cnt[kCntOutcome + i]) atomicAdd(cnt + 2 + i, s_cnt[kCntOutcome + i]);
-    if (s_cnt[kCntDouble]) atomicAdd(cnt + 7, s_cnt[kCntDouble]);
-    if (want_scats) {
-      if (s_rows[0]) atomicAdd(cnt + 8, s_rows[0]);
-      if (s_rows[1]) atomicAdd(cnt + 9, s_rows[1]);
+  flush_block_stats(O, s_hist, s_cnt, s_rows, want_scats, want_chan);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K1p: trajectory_DS without row recording (statistics + els rows only): table events go through a warp-private
+// PARK POOL in shared memory.
+//
+// 12 % of the DS events (Moller / Gryzinski) need an inverse-CDF table search = a chain of three dependent memory
+// accesses executed by ~4 of the 32 lanes; in traj_kernel 98 % of the warp-iterations pay that chain (40 % of the
+// stall samples, 12 % of the warp instructions at 3.4 lanes).  Here a lane whose event picked a table channel PARKS
+// its electron (state + the two uniforms it still needs, 14 words) in the warp's pool and takes another electron at
+// once.  When 32 electrons are parked the warp runs one BATCH iteration: the lanes swap their current electrons into
+// the pool (as 'ready' entries) for the 32 parked ones and all 32 lanes search together -- one converged chain per 32
+// table events instead of one per warp-iteration.  Ready entries re-enter lanes as lanes park or retire.  Results do
+// not depend on any of this: the uniforms of an event are a function of (seed, electron id, event index).
+//
+// Pool layout (per warp, word-major so that lanes hit distinct banks): slots [0, n_ready) hold ready electrons,
+// slots [kPoolSlots - n_pend, kPoolSlots) hold parked ones (a stack growing downwards).
+// ---------------------------------------------------------------------------------------------------------------
+#ifndef MCD_POOL_SLOTS
+#define MCD_POOL_SLOTS 64
+#endif
+constexpr int kPoolSlots = MCD_POOL_SLOTS;
+constexpr int kPoolWords = 14;       // E x y z dx dy dz yx yy yz | rel_id | ev + slot/outcome/exact bits | u.z | u.w
+
+#define MCD_POOL_EACH_STATE(OP) \
+  OP(0, e.E) OP(1, e.x) OP(2, e.y) OP(3, e.z) OP(4, e.dx) OP(5, e.dy) OP(6, e.dz) OP(7, e.yx) OP(8, e.yy) OP(9, e.yz)
+
+template <int S, bool RESUME>
+__global__ void __launch_bounds__(kThreads, MCD_MIN_BLOCKS)
+traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsigned long long first_id,
+                 const unsigned long long count_arg) {
+  // RESUME pass: the "ids" are the entries of the leftover queue the previous pass wrote; only as many blocks as
+  // are needed to give every lane two electrons (lanes + pool) do any work
+  const unsigned long long count = RESUME ? *O.rq_in_count : count_arg;
+  if (RESUME && (unsigned long long)blockIdx.x * (2ull * kThreads) >= count) return;
+  __shared__ unsigned int s_hist[MCD_HIST_TOTAL];
+  __shared__ unsigned long long s_cnt[kCntTotal];
+  __shared__ uint32_t s_pool[kThreads / 32][kPoolWords * kPoolSlots];
+
+  for (int i = threadIdx.x; i < MCD_HIST_TOTAL; i += kThreads) s_hist[i] = 0u;
+  for (int i = threadIdx.x; i < kCntTotal; i += kThreads) s_cnt[i] = 0ull;
+  __syncthreads();
+
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned lt = lanemask_lt();
+  const bool want_hist = (P.flags & MCD_FLAG_HISTOGRAMS) != 0u;
+  const bool want_chan = (P.flags & MCD_FLAG_CHANNEL_COUNTS) != 0u;
+  uint32_t* const pool = s_pool[threadIdx.x >> 5];
+  int n_ready = 0, n_pend = 0;                   // warp-uniform
+  bool exhausted = false;                        // warp-uniform: the ticket ran past `count`
+
+  bool alive = false;
+  ElState e;
+  uint32_t rel_id = 0u, ev = 0u;
+
+  while (true) {
+    // ---- refill dead lanes: ready electrons of the pool first, then fresh ones (multiScatter.py:105-107) ------
+    const unsigned need = __ballot_sync(MCD_FULL_MASK, !alive);
+    if (need) {
+      const int nneed = __popc(need);
+      const int rank = __popc(need & lt);
+      const int take = min(nneed, n_ready);
+      if (take > 0) {
+        if (!alive && rank < take) {
+          const uint32_t* q = pool + (n_ready - 1 - rank);
+#define MCD_LD(w, f) f = __uint_as_float(q[(w) * kPoolSlots]);
+          MCD_POOL_EACH_STATE(MCD_LD)
+#undef MCD_LD
+          rel_id = q[10 * kPoolSlots];
+          ev = q[11 * kPoolSlots];
+          alive = true;
+        }
+        n_ready -= take;
+      }
+      const int nreq = nneed - take;
+      if (nreq > 0 && !exhausted) {
+        const unsigned still = __ballot_sync(MCD_FULL_MASK, !alive);
+        const int leader = __ffs(still) - 1;
+        unsigned long long base = 0ull;
+        if ((int)lane == leader) base = atomicAdd(O.ticket, (unsigned long long)nreq);
+        base = __shfl_sync(MCD_FULL_MASK, base, leader);
+        if (!alive) {
+          const unsigned long long rid = base + (unsigned long long)(rank - take);
+          if (rid < count) {
+            alive = true;
+            if (RESUME) {                                          // an electron the previous pass handed over
+              const uint32_t* q = O.rq_in + rid;
+#define MCD_LDQ(w, f) f = __uint_as_float(__ldcs(q + (size_t)(w) * O.rq_cap));
+              MCD_POOL_EACH_STATE(MCD_LDQ)
+#undef MCD_LDQ
+              rel_id = __ldcs(q + (size_t)10 * O.rq_cap);
+              ev = __ldcs(q + (size_t)11 * O.rq_cap);
+            } else {
+              rel_id = (uint32_t)rid;
+              ev = 0u;
+              e.E = P.E0;
+              e.x = 0.f; e.y = 0.f; e.z = 0.f;
+              e.dx = P.d0x; e.dy = P.d0y; e.dz = P.d0z;
+              e.yx = 0.f; e.yy = 1.f; e.yz = 0.f;                  // electron.py:38
+            }
+          }
+        }
+        exhausted = (base + (unsigned long long)nreq >= count);
+      }
     }
-    if (s_cnt[kCntNan]) atomicAdd(cnt + 10, s_cnt[kCntNan]);
-    if (s_cnt[kCntExact]) atomicAdd(cnt + 11, s_cnt[kCntExact]);
-    if (want_chan)
-      for (int i = 0; i < MCD_MAX_CHANNELS; ++i)
-        if (s_cnt[kCntChan + i]) atomicAdd(cnt + 12 + i, s_cnt[kCntChan + i]);
+    const unsigned am = __ballot_sync(MCD_FULL_MASK, alive);
+    const int a = __popc(am);
+    if (a == 0 && n_pend == 0) break;
+    // ---- tail: once the ids have run out a warp that is down to dump_T electrons hands them to the next pass
+    // (leftover queue in global memory) and leaves; that pass runs them in full warps again.  A trajectory is
+    // 7..870 events long, so without this every warp (and its block's slot on the SM) lingers for ~800 iterations
+    // at an average of 12 live lanes.  Parked electrons are searched first (forced batch), so the queue only holds
+    // plain states. ---------------------------------------------------------------------------------------------
+    const bool tail = exhausted && (a + n_pend <= O.dump_T);
+    if (tail && n_pend == 0) {
+      const int leader = __ffs(am) - 1;
+      unsigned long long base = 0ull;
+      if ((int)lane == leader) base = atomicAdd(O.rq_out_count, (unsigned long long)a);
+      base = __shfl_sync(MCD_FULL_MASK, base, leader);
+      if (alive) {
+        uint32_t* q = O.rq_out + (base + (unsigned long long)__popc(am & lt));
+#define MCD_STQ(w, f) q[(size_t)(w) * O.rq_cap] = __float_as_uint(f);
+        MCD_POOL_EACH_STATE(MCD_STQ)
+#undef MCD_STQ
+        q[(size_t)10 * O.rq_cap] = rel_id;
+        q[(size_t)11 * O.rq_cap] = ev;
+      }
+      break;
+    }
+
+    bool done = false;                             // this lane completes an event in this iteration
+    int outcome = -1, slot = 0, flags = 0;
+    float W = 0.f, om = 0.f, uphi = 0.f;
+    if (n_pend > 0 && (n_pend >= a || tail)) {
+      // ---- BATCH iteration: current electrons -> ready entries, parked electrons -> lanes, then search ----------
+      // (the two pool regions may overlap, so every word is read by all lanes before it is overwritten; a <= nb
+      // except in the forced batch of the tail, where the pool is nearly empty)
+      const int nb = min(n_pend, 32);
+      const bool ld = (int)lane < nb;
+      const uint32_t* q = pool + (kPoolSlots - n_pend + (int)lane);
+      uint32_t* w = pool + (n_ready + __popc(am & lt));
+      uint32_t t;
+#define MCD_SWAP(i, f) t = ld ? q[(i) * kPoolSlots] : 0u; __syncwarp(); if (alive) w[(i) * kPoolSlots] = __float_as_uint(f); f = __uint_as_float(t);
+      MCD_POOL_EACH_STATE(MCD_SWAP)
+#undef MCD_SWAP
+      t = ld ? q[10 * kPoolSlots] : 0u; __syncwarp(); if (alive) w[10 * kPoolSlots] = rel_id; rel_id = t;
+      t = ld ? q[11 * kPoolSlots] : 0u; __syncwarp(); if (alive) w[11 * kPoolSlots] = ev; ev = t;
+      const float uz = ld ? __uint_as_float(q[12 * kPoolSlots]) : 0.f;
+      uphi = ld ? __uint_as_float(q[13 * kPoolSlots]) : 0.f;
+      n_ready += a;
+      n_pend -= nb;
+      alive = ld;
+      __syncwarp();
+      if (ld) {
+        slot = (int)((ev >> 24) & 15u);
+        outcome = (int)((ev >> 28) & 7u) - 1;
+        flags = (int)(ev >> 31);                   // MCD_EVF_EXACT = 1
+        ev &= 0xffffffu;
+        int tab = MCD_TABLE_MOLLER;
+        if (slot >= 3) tab = P.gryz_per_shell ? (MCD_TABLE_GRYZ0 + (S - 1 - P.m.gShell[slot - 3])) : MCD_TABLE_GRYZ0;
+        ds_table_loss(P, e, tab, uz, flags, W, om);
+        done = true;
+      }
+    } else {
+      // ---- normal iteration of trajectory_DS: an alive lane executes one event or, past maxScatt, retires as
+      // 'long' (singleScatter.py:19-23); a lane whose event needs a table parks its electron -----------------------
+      const bool has_row = alive && (ev < (uint32_t)P.maxScatt);
+      if (alive && !has_row) outcome = MCD_OUT_LONG;
+      bool park = false;
+      float uz = 0.f;
+      EventRow row;
+      if (has_row) {
+        const float4 u = event_uniforms(P, first_id + rel_id, ev);
+        EventMid mid;
+        ds_phase_a<S>(P, e, u, row, mid);
+        outcome = row.outcome;
+        slot = row.slot;
+        flags = row.flags;
+        uphi = u.w;
+        W = mid.W;
+        om = mid.om;
+        uz = u.z;
+        park = mid.tab >= 0;
+        done = !park;
+      }
+      const unsigned pm = __ballot_sync(MCD_FULL_MASK, park);
+      if (pm) {
+        const int room = kPoolSlots - n_ready - n_pend;
+        const int r = __popc(pm & lt);
+        if (park) {
+          if (r < room) {
+            uint32_t* w = pool + (kPoolSlots - n_pend - 1 - r);
+#define MCD_ST(i, f) w[(i) * kPoolSlots] = __float_as_uint(f);
+            MCD_POOL_EACH_STATE(MCD_ST)
+#undef MCD_ST
+            w[10 * kPoolSlots] = rel_id;
+            w[11 * kPoolSlots] = ev | ((uint32_t)slot << 24) | ((uint32_t)(outcome + 1) << 28) | ((uint32_t)(flags & 1) << 31);
+            w[12 * kPoolSlots] = __float_as_uint(uz);
+            w[13 * kPoolSlots] = __float_as_uint(uphi);
+            alive = false;
+          } else {
+            // pool full (practically never): undo the position update; the lane repeats this event next iteration
+            e.x = row.px; e.y = row.py; e.z = row.pz;
+          }
+          outcome = -1;
+        }
+        n_pend += min(__popc(pm), room);
+        __syncwarp();
+      }
+    }
+
+    // ---- energy update (electron.py:44-59), retire (saveOutcomes before the rotation), update_direction ---------
+    const float preE = e.E;
+    const float c2 = 1.0f - om;
+    if (done) {
+      const float En = preE - W;
+      if (En <= P.Emin) {
+        if (outcome < 0) outcome = MCD_OUT_ABS;
+        else flags |= MCD_EVF_DOUBLE;               // reference records a second 'abs' row (Q4)
+      }
+      e.E = En;
+    }
+    if (outcome >= 0) {
+      retire_lane(P, O, s_hist, s_cnt, want_hist, outcome, (flags & MCD_EVF_DOUBLE) != 0, preE, e, rel_id,
+                  ev + (done ? 1u : 0u));
+      alive = false;
+    }
+    if (done) {
+      rotate_dir(e.dx, e.dy, e.dz, e.yx, e.yy, e.yz, c2, om, uphi);
+      if (want_chan) atomicAdd(&s_cnt[kCntChan + slot_channel(P.m, slot)], 1ull);
+      if (flags & (MCD_EVF_NANCLAMP | MCD_EVF_EXACT)) {
+        if (flags & MCD_EVF_NANCLAMP) atomicAdd(&s_cnt[kCntNan], 1ull);
+        if (flags & MCD_EVF_EXACT) atomicAdd(&s_cnt[kCntExact], 1ull);
+      }
+      ++ev;
+    }
   }
+
+  __syncthreads();
+  flush_block_stats(O, s_hist, s_cnt, nullptr, false, want_chan);
 }
 
 typedef void (*TrajKernel)(const DevParams, const DevOut, const unsigned long long, const unsigned long long);
@@ -254,8 +509,31 @@ TrajKernel pick_kernel_t(const DevParams& P) {
   }
 }
 
+template <bool RESUME>
+TrajKernel pick_kernel_pool(const DevParams& P) {
+  switch (P.m.nshell) {
+    case 1: return traj_kernel_pool<1, RESUME>;
+    case 2: return traj_kernel_pool<2, RESUME>;
+    case 3: return traj_kernel_pool<3, RESUME>;
+    case 4: return traj_kernel_pool<4, RESUME>;
+    case 5: return traj_kernel_pool<5, RESUME>;
+    case 6: return traj_kernel_pool<6, RESUME>;
+    case 7: return traj_kernel_pool<7, RESUME>;
+    case 8: return traj_kernel_pool<8, RESUME>;
+    default: return nullptr;
+  }
+}
+
+bool pool_enabled() {      // MCD_NO_POOL=1: the plain kernel for statistics-only DS runs too (A/B measurements)
+  static const bool no_pool = getenv("MCD_NO_POOL") != nullptr && atoi(getenv("MCD_NO_POOL")) != 0;
+  return !no_pool;
+}
+
 TrajKernel pick_kernel(const DevParams& P, bool scats) {
-  return scats ? pick_kernel_t<true>(P) : pick_kernel_t<false>(P);
+  if (scats) return pick_kernel_t<true>(P);
+  // statistics-only DS runs use the park-pool kernel
+  if (P.mode == MCD_MODE_DS && pool_enabled()) return pick_kernel_pool<false>(P);
+  return pick_kernel_t<false>(P);
 }
 
 }  // namespace
@@ -399,9 +677,8 @@ unsigned long long mcd_order_tiles(unsigned long long count) {
   return (count + 1 + per_tile - 1) / per_tile;
 }
 
-cudaError_t mcd_traj_max_blocks(const DevParams& P, int sm_count, TrajLaunchInfo* info) {
-  // both variants have the same launch bounds; the occupancy of the row-writing one is reported
-  TrajKernel k = pick_kernel(P, true);
+cudaError_t mcd_traj_max_blocks(const DevParams& P, bool scats, int sm_count, TrajLaunchInfo* info) {
+  TrajKernel k = pick_kernel(P, scats);
   if (!k) return cudaErrorInvalidValue;
   int per_sm = 0;
   cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kThreads, 0);
@@ -414,21 +691,69 @@ cudaError_t mcd_traj_max_blocks(const DevParams& P, int sm_count, TrajLaunchInfo
     const int v = atoi(env);
     if (v >= 1 && v < per_sm) per_sm = v;
   }
+  // shared-memory carve-out: exactly what the resident blocks need (+1 KB per block that the system reserves), the
+  // rest of the 256 KB stays L1 for the cross-section cells and the table windows
+  const size_t need = (size_t)per_sm * (fa.sharedSizeBytes + 1024);
+  int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
+  if (pct > 100) pct = 100;
+  cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
   info->blocks = per_sm * sm_count;
   info->threads = kThreads;
   info->regs = fa.numRegs;
   info->blocks_per_sm = per_sm;
+  info->launches = 1;
   return cudaSuccess;
 }
 
-cudaError_t mcd_launch_traj(const DevParams& P, const DevOut& O, unsigned long long first_id,
+int mcd_traj_uses_queue(const DevParams& P, bool scats) {
+  return (!scats && P.mode == MCD_MODE_DS && pool_enabled()) ? 1 : 0;
+}
+
+cudaError_t mcd_launch_traj(const DevParams& P, const DevOut& O_in, unsigned long long first_id,
                             unsigned long long count, int sm_count, cudaStream_t stream, TrajLaunchInfo* info) {
-  TrajKernel k = pick_kernel(P, (P.scat_row_words > 0) && (O.scats != nullptr));
+  const bool scats = (P.scat_row_words > 0) && (O_in.scats != nullptr);
+  TrajKernel k = pick_kernel(P, scats);
   if (!k) return cudaErrorInvalidValue;
   TrajLaunchInfo li;
-  cudaError_t err = mcd_traj_max_blocks(P, sm_count, &li);
+  cudaError_t err = mcd_traj_max_blocks(P, scats, sm_count, &li);
   if (err != cudaSuccess) return err;
+  DevOut O = O_in;
+  // tail hand-over (park-pool kernel only): pass 0 runs the fresh ids and dumps what its warps still hold when they
+  // are down to dump_T electrons; passes 1..n-1 run the leftover queue of the pass before; the last pass does not
+  // dump.  MCD_DUMP_T=0 or MCD_PASSES=1: one launch.
+  static const int env_T = getenv("MCD_DUMP_T") ? atoi(getenv("MCD_DUMP_T")) : 24;
+  static const int env_passes = getenv("MCD_PASSES") ? atoi(getenv("MCD_PASSES")) : 3;
+  int passes = 1;
+  int dump_T = 0;
+  if (mcd_traj_uses_queue(P, scats) && O_in.rq[0] && env_T > 0 && env_passes > 1) {
+    passes = env_passes > 4 ? 4 : env_passes;
+    dump_T = env_T > 31 ? 31 : env_T;
+  }
+  li.launches = passes;
   if (info) *info = li;
-  k<<<li.blocks, kThreads, 0, stream>>>(P, O, first_id, count);
-  return cudaGetLastError();
+  for (int p = 0; p < passes; ++p) {
+    const bool last = (p == passes - 1);
+    O.ticket = O_in.ticket + p;
+    O.rq_in = p ? O_in.rq[(p - 1) & 1] : nullptr;
+    O.rq_in_count = p ? O_in.rq_counts + (p - 1) : nullptr;
+    O.rq_out = last ? nullptr : O_in.rq[p & 1];
+    O.rq_out_count = last ? nullptr : O_in.rq_counts + p;
+    O.dump_T = last ? -1 : dump_T;
+    if (p == 0) {
+      k<<<li.blocks, kThreads, 0, stream>>>(P, O, first_id, count);
+    } else {
+      TrajKernel kr = pick_kernel_pool<true>(P);
+      // same shared-memory carve-out as the first pass
+      cudaFuncAttributes fa;
+      if (cudaFuncGetAttributes(&fa, kr) == cudaSuccess) {
+        const size_t need = (size_t)li.blocks_per_sm * (fa.sharedSizeBytes + 1024);
+        int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
+        cudaFuncSetAttribute(kr, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
+      }
+      kr<<<li.blocks, kThreads, 0, stream>>>(P, O, first_id, count);
+    }
+    err = cudaGetLastError();
+    if (err != cudaSuccess) return err;
+  }
+  return cudaSuccess;
 }

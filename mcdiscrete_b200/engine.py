@@ -305,7 +305,10 @@ class Engine:
     def launch_info(self):
         b, t, r, o = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         self._ck(self.lib.mcd_launch_info(self.ctx, C.byref(b), C.byref(t), C.byref(r), C.byref(o)))
-        return {'blocks': b.value, 'threads': t.value, 'regs': r.value, 'blocks_per_sm': o.value}
+        n = C.c_int()
+        self._ck(self.lib.mcd_last_launches(self.ctx, C.byref(n)))
+        return {'blocks': b.value, 'threads': t.value, 'regs': r.value, 'blocks_per_sm': o.value,
+                'launches_per_run': n.value}
 
     def drain(self, first_id, count, want_els=True, want_scats=True, pinned=False, stream=None, ordered=False):
         """Copy the rows of the last run to host arrays.  ordered=True regroups the scats rows on the device
