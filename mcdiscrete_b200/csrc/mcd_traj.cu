@@ -268,10 +268,25 @@ traj_kernel(const __grid_constant__ DevParams P, const DevOut O, const unsigned 
 // slots [kPoolSlots - n_pend, kPoolSlots) hold parked ones (a stack growing downwards).
 // ---------------------------------------------------------------------------------------------------------------
 #ifndef MCD_POOL_SLOTS
-#define MCD_POOL_SLOTS 64
+#define MCD_POOL_SLOTS 48
 #endif
 constexpr int kPoolSlots = MCD_POOL_SLOTS;
+#ifndef MCD_BATCH_MIN
+#define MCD_BATCH_MIN 32             // parked electrons that trigger a batch iteration (<= 32)
+#endif
+constexpr int kBatchMin = MCD_BATCH_MIN;
 constexpr int kPoolWords = 14;       // E x y z dx dy dz yx yy yz | rel_id | ev + slot/outcome/exact bits | u.z | u.w
+
+// out-of-line copy of the table search for the pool-full case (keeps the hot loop's code small)
+static __device__ __noinline__ float2 table_loss_call(const DevParams& P, float E, int tab, float uz, int* flags) {
+  ElState t;
+  t.E = E;
+  float W, om;
+  int f = *flags;
+  ds_table_loss(P, t, tab, uz, f, W, om);
+  *flags = f;
+  return make_float2(W, om);
+}
 
 #define MCD_POOL_EACH_STATE(OP) \
   OP(0, e.E) OP(1, e.x) OP(2, e.y) OP(3, e.z) OP(4, e.dx) OP(5, e.dy) OP(6, e.dz) OP(7, e.yx) OP(8, e.yy) OP(9, e.yz)
@@ -382,25 +397,28 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
     bool done = false;                             // this lane completes an event in this iteration
     int outcome = -1, slot = 0, flags = 0;
     float W = 0.f, om = 0.f, uphi = 0.f;
-    if (n_pend > 0 && (n_pend >= a || tail)) {
+    if (n_pend > 0 && (n_pend >= min(a, kBatchMin) || tail)) {
       // ---- BATCH iteration: current electrons -> ready entries, parked electrons -> lanes, then search ----------
       // (the two pool regions may overlap, so every word is read by all lanes before it is overwritten; a <= nb
       // except in the forced batch of the tail, where the pool is nearly empty)
       const int nb = min(n_pend, 32);
       const bool ld = (int)lane < nb;
+      // lanes >= nb keep their electron and sit this iteration out (only when fewer than 32 are parked)
+      const bool st = alive && (ld || tail);
+      const unsigned sm = __ballot_sync(MCD_FULL_MASK, st);
       const uint32_t* q = pool + (kPoolSlots - n_pend + (int)lane);
-      uint32_t* w = pool + (n_ready + __popc(am & lt));
+      uint32_t* w = pool + (n_ready + __popc(sm & lt));
       uint32_t t;
-#define MCD_SWAP(i, f) t = ld ? q[(i) * kPoolSlots] : 0u; __syncwarp(); if (alive) w[(i) * kPoolSlots] = __float_as_uint(f); f = __uint_as_float(t);
+#define MCD_SWAP(i, f) t = ld ? q[(i) * kPoolSlots] : 0u; __syncwarp(); if (st) w[(i) * kPoolSlots] = __float_as_uint(f); if (ld) f = __uint_as_float(t);
       MCD_POOL_EACH_STATE(MCD_SWAP)
 #undef MCD_SWAP
-      t = ld ? q[10 * kPoolSlots] : 0u; __syncwarp(); if (alive) w[10 * kPoolSlots] = rel_id; rel_id = t;
-      t = ld ? q[11 * kPoolSlots] : 0u; __syncwarp(); if (alive) w[11 * kPoolSlots] = ev; ev = t;
+      t = ld ? q[10 * kPoolSlots] : 0u; __syncwarp(); if (st) w[10 * kPoolSlots] = rel_id; if (ld) rel_id = t;
+      t = ld ? q[11 * kPoolSlots] : 0u; __syncwarp(); if (st) w[11 * kPoolSlots] = ev; if (ld) ev = t;
       const float uz = ld ? __uint_as_float(q[12 * kPoolSlots]) : 0.f;
       uphi = ld ? __uint_as_float(q[13 * kPoolSlots]) : 0.f;
-      n_ready += a;
+      n_ready += __popc(sm);
       n_pend -= nb;
-      alive = ld;
+      alive = ld || (alive && !st);
       __syncwarp();
       if (ld) {
         slot = (int)((ev >> 24) & 15u);
@@ -449,11 +467,16 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
             w[12 * kPoolSlots] = __float_as_uint(uz);
             w[13 * kPoolSlots] = __float_as_uint(uphi);
             alive = false;
+            outcome = -1;
           } else {
-            // pool full (practically never): undo the position update; the lane repeats this event next iteration
-            e.x = row.px; e.y = row.py; e.z = row.pz;
+            // pool full (rare): this lane searches its table at once, like traj_kernel does for every table event
+            int tab = MCD_TABLE_MOLLER;
+            if (slot >= 3) tab = P.gryz_per_shell ? (MCD_TABLE_GRYZ0 + (S - 1 - P.m.gShell[slot - 3])) : MCD_TABLE_GRYZ0;
+            const float2 r2 = table_loss_call(P, e.E, tab, uz, &flags);
+            W = r2.x;
+            om = r2.y;
+            done = true;
           }
-          outcome = -1;
         }
         n_pend += min(__popc(pm), room);
         __syncwarp();

@@ -92,10 +92,13 @@ def main():
             env['MCD_LIB'] = os.path.abspath(var)
         else:
             env.update(dict(kv.split('=', 1) for kv in var.split(',')))
-        r = subprocess.run([sys.executable, os.path.abspath(__file__), '--child', '--workload', a.workload, '--n', str(a.n),
-                            '--reps', str(a.reps), '--tag', var, '--pipes', ','.join(map(str, a.pipes))],
-                           env=env, capture_output=True, text=True)
-        sys.stdout.write(r.stdout if r.returncode == 0 else 'FAILED %s\n%s\n' % (var, r.stderr[-2000:]))
+        cmd = [sys.executable, os.path.abspath(__file__), '--child', '--workload', a.workload, '--n', str(a.n),
+               '--reps', str(a.reps), '--tag', var, '--pipes', ','.join(map(str, a.pipes))]
+        try:      # a variant that hangs must not eat the GPU budget
+            r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=120)
+            sys.stdout.write(r.stdout if r.returncode == 0 else 'FAILED %s\n%s\n' % (var, r.stderr[-2000:]))
+        except subprocess.TimeoutExpired:
+            sys.stdout.write('TIMEOUT %s\n' % var)
         sys.stdout.flush()
 
 
