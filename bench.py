@@ -211,10 +211,13 @@ def main():
     torch.cuda.synchronize()
     t_tables = time.time() - t0
     table_bytes = sum(4 * len(T.Es) * (len(T.Ws) - 1) for T in [tabs['Moller']] + tabs['Gryz'])
-    # two contexts sharing the tables, one CUDA stream each: consecutive steps are pipelined, so the blocks of
-    # step k+1 fill the SMs that the tail of step k leaves idle (1e6 electrons are only 6.6 per resident lane)
-    engs = [eng, eng.clone()]
-    tstreams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    # NPIPE contexts sharing the tables, one CUDA stream each: consecutive steps are pipelined, so the blocks of
+    # step k+1 fill the SMs that the tail of step k leaves idle (1e6 electrons are only 5.9 per resident lane) and
+    # the tail hand-over passes of one step (sparse: the last electrons of a step are serial chains of up to
+    # ~870 events) run behind the main pass of another
+    NPIPE = 4
+    engs = [eng] + [eng.clone() for _ in range(NPIPE - 1)]
+    tstreams = [torch.cuda.Stream() for _ in range(NPIPE)]
     for e in engs:
         e.set_capacity(n_el, 0)
     stream = torch.cuda.current_stream().cuda_stream
@@ -239,12 +242,12 @@ def main():
         return fid
 
     def device_step(k):
-        e, ts = engs[k % 2], tstreams[k % 2]
+        e, ts = engs[k % NPIPE], tstreams[k % NPIPE]
         with torch.cuda.stream(ts):
             e.reset_stats(ts.cuda_stream)
             e.launch(first_id(), n_el, ts.cuda_stream)
             if world > 1:
-                allreduce_stats(stats[k % 2])
+                allreduce_stats(stats[k % NPIPE])
 
     # ---- device-timed throughput ------------------------------------------------------------------------
     for k in range(args.warmup):
@@ -255,23 +258,24 @@ def main():
     time.sleep(0.3)
     kernel_ms = []
     ev0 = torch.cuda.Event(enable_timing=True)
-    ev1 = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(NPIPE)]
     tw0 = time.time()
     ev0.record(tstreams[0])
-    tstreams[1].wait_event(ev0)                      # both streams start after the same timestamp
+    for ts in tstreams[1:]:
+        ts.wait_event(ev0)                           # all streams start after the same timestamp
     for k in range(args.steps):
         device_step(k)
-    ev1[0].record(tstreams[0])
-    ev1[1].record(tstreams[1])
+    for ts, e1 in zip(tstreams, ev1):
+        e1.record(ts)
     barrier()
     tw1 = time.time()
-    ms = max(ev0.elapsed_time(ev1[0]), ev0.elapsed_time(ev1[1]))
+    ms = max(ev0.elapsed_time(e1) for e1 in ev1)
     clocks = sampler.stop(tw0, tw1)
     tmax = torch.tensor([ms], device='cuda')
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms = float(tmax.item())
-    cnt = engs[(args.steps - 1) % 2].counters()   # of the last step (summed over ranks when world > 1)
+    cnt = engs[(args.steps - 1) % NPIPE].counters()   # of the last step (summed over ranks when world > 1)
     events_per_step = cnt['events']           # whole job
     electrons_per_step = cnt['electrons_done']
     assert electrons_per_step == n_el * world, (electrons_per_step, n_el, world)
@@ -285,8 +289,14 @@ def main():
         eng.sync(stream)
         kernel_ms.append(eng.kernel_ms())
     k_ms = sum(kernel_ms) / len(kernel_ms)
+    launches = eng.launch_info()['launches_per_run']
     ev_local = eng.counters()['events']
-    ev_rate = ev_local / (k_ms * 1e-3)        # this rank's kernel
+    # roofline timing: the trajectory launches are the only kernels of a step, so the per-step device time of the
+    # timed region above (steps overlapping on NPIPE streams, CUDA events on the launch streams) IS the average
+    # duration of one step's launches under the conditions the throughput is quoted for; the serial stand-alone
+    # duration of one step's launches (k_ms, includes its un-overlapped tail) is reported beside it
+    step_ms = ms / args.steps
+    ev_rate = ev_local / (step_ms * 1e-3)     # this rank
     fp32_ach = ev_rate * FLOPS_PER_EVENT / 1e12
     mufu_ach = ev_rate * MUFU_PER_EVENT / 1e12
     fp32_frac, mufu_frac = fp32_ach / f32p.value, mufu_ach / mufu.value
@@ -303,7 +313,9 @@ def main():
                 'peak': mufu.value if bound == 'mufu' else f32p.value,
                 'unit': 'Ttranscendental/s' if bound == 'mufu' else 'TFLOP/s',
                 'frac': max(mufu_frac, fp32_frac), 'traffic': traffic,
-                'kernel': 'traj_kernel<3,DS>', 'kernel_ms': k_ms, 'events_per_launch': ev_local,
+                'kernel': 'traj_kernel_pool<3> (main pass + %d tail hand-over passes of the same kernel)' % (launches - 1),
+                'kernel_ms': step_ms, 'kernel_ms_standalone': k_ms, 'events_per_launch': ev_local,
+                'timing': 'per-step device time inside the pipelined timed region; standalone = one step launched alone',
                 'fp32': {'achieved_tflops': fp32_ach, 'peak_tflops': f32p.value, 'frac': fp32_frac,
                          'flops_per_event': FLOPS_PER_EVENT},
                 'mufu': {'achieved_tops': mufu_ach, 'peak_tops': mufu.value, 'frac': mufu_frac,
@@ -311,8 +323,8 @@ def main():
                 'peak_source': 'measured on this GPU by mcd_measure_peaks (FFMA / MUFU.EX2 dependent chains); '
                                'MEASURED_PEAKS.json has no FP32/MUFU figure',
                 'hbm': {'table_bytes_resident': table_bytes, 'peak_gbs_measured': 6547.2,
-                        'achieved_gbs': (traffic / (k_ms * 1e-3) / 1e9) if traffic else None,
-                        'frac': (traffic / (k_ms * 1e-3) / 1e9 / 6547.2) if traffic else None,
+                        'achieved_gbs': (traffic / (step_ms * 1e-3) / 1e9) if traffic else None,
+                        'frac': (traffic / (step_ms * 1e-3) / 1e9 / 6547.2) if traffic else None,
                         'note': 'DRAM traffic of the trajectory kernel (ncu) over its CUDA-event duration; the kernel is '
                                 'issue-bound, HBM is second order'}}
 
@@ -350,9 +362,9 @@ def main():
                        'outputs': 'one els row per electron + fused backscatter histograms + counters',
                        'cache': 'inputs larger than L2 (inverse-CDF tables %.2f GB resident in HBM)' % (table_bytes / 1e9),
                        'parallelism': 'electron ids partitioned across %d GPU(s); int64 histogram all-reduce' % world,
-                       'pipelining': 'steps alternate between two contexts / two streams (shared tables)'},
+                       'pipelining': 'steps rotate over %d contexts / streams (shared tables); %d launches per step (main pass + tail hand-over passes)' % (NPIPE, launches)},
             'e2e': {'value': e2e, 'unit': 'electrons/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
-            'gpu_launches': args.steps,
+            'gpu_launches': args.steps * launches,
             'clocks': clocks,
             'roofline': roofline,
             'setup': {'tables_s': t_tables, 'table_shapes': {'Moller': [len(tabs['Moller'].Es), len(tabs['Moller'].Ws)],

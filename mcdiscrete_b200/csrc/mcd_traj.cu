@@ -264,8 +264,8 @@ traj_kernel(const __grid_constant__ DevParams P, const DevOut O, const unsigned 
 // table events instead of one per warp-iteration.  Ready entries re-enter lanes as lanes park or retire.  Results do
 // not depend on any of this: the uniforms of an event are a function of (seed, electron id, event index).
 //
-// Pool layout (per warp, word-major so that lanes hit distinct banks): slots [0, n_ready) hold ready electrons,
-// slots [kPoolSlots - n_pend, kPoolSlots) hold parked ones (a stack growing downwards).
+// Pool layout (per warp): slots of kSlotWords words moved with 128-bit shared-memory accesses; slots [0, n_ready)
+// hold ready electrons, slots [kPoolSlots - n_pend, kPoolSlots) hold parked ones (a stack growing downwards).
 // ---------------------------------------------------------------------------------------------------------------
 #ifndef MCD_POOL_SLOTS
 #define MCD_POOL_SLOTS 48
@@ -275,7 +275,8 @@ constexpr int kPoolSlots = MCD_POOL_SLOTS;
 #define MCD_BATCH_MIN 32             // parked electrons that trigger a batch iteration (<= 32)
 #endif
 constexpr int kBatchMin = MCD_BATCH_MIN;
-constexpr int kPoolWords = 14;       // E x y z dx dy dz yx yy yz | rel_id | ev + slot/outcome/exact bits | u.z | u.w
+constexpr int kSlotWords = 20;       // 14 used: E x y z | dx dy dz yx | yy yz rel_id ev+bits | u.z u.w; a stride of 20
+                                     // words keeps the 128-bit accesses of 8 consecutive slots on distinct banks
 
 // out-of-line copy of the table search for the pool-full case (keeps the hot loop's code small)
 static __device__ __noinline__ float2 table_loss_call(const DevParams& P, float E, int tab, float uz, int* flags) {
@@ -286,6 +287,22 @@ static __device__ __noinline__ float2 table_loss_call(const DevParams& P, float 
   ds_table_loss(P, t, tab, uz, f, W, om);
   *flags = f;
   return make_float2(W, om);
+}
+
+__device__ __forceinline__ void pool_put(uint32_t* slot, const ElState& e, uint32_t rel_id, uint32_t evw) {
+  uint4* p = reinterpret_cast<uint4*>(slot);
+  p[0] = make_uint4(__float_as_uint(e.E), __float_as_uint(e.x), __float_as_uint(e.y), __float_as_uint(e.z));
+  p[1] = make_uint4(__float_as_uint(e.dx), __float_as_uint(e.dy), __float_as_uint(e.dz), __float_as_uint(e.yx));
+  p[2] = make_uint4(__float_as_uint(e.yy), __float_as_uint(e.yz), rel_id, evw);
+}
+
+__device__ __forceinline__ void pool_unpack(const uint4& a, const uint4& b, const uint4& c, ElState& e,
+                                            uint32_t& rel_id, uint32_t& evw) {
+  e.E = __uint_as_float(a.x); e.x = __uint_as_float(a.y); e.y = __uint_as_float(a.z); e.z = __uint_as_float(a.w);
+  e.dx = __uint_as_float(b.x); e.dy = __uint_as_float(b.y); e.dz = __uint_as_float(b.z); e.yx = __uint_as_float(b.w);
+  e.yy = __uint_as_float(c.x); e.yz = __uint_as_float(c.y);
+  rel_id = c.z;
+  evw = c.w;
 }
 
 #define MCD_POOL_EACH_STATE(OP) \
@@ -301,7 +318,7 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
   if (RESUME && (unsigned long long)blockIdx.x * (2ull * kThreads) >= count) return;
   __shared__ unsigned int s_hist[MCD_HIST_TOTAL];
   __shared__ unsigned long long s_cnt[kCntTotal];
-  __shared__ uint32_t s_pool[kThreads / 32][kPoolWords * kPoolSlots];
+  __shared__ __align__(16) uint32_t s_pool[kThreads / 32][kSlotWords * kPoolSlots];
 
   for (int i = threadIdx.x; i < MCD_HIST_TOTAL; i += kThreads) s_hist[i] = 0u;
   for (int i = threadIdx.x; i < kCntTotal; i += kThreads) s_cnt[i] = 0ull;
@@ -328,12 +345,8 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
       const int take = min(nneed, n_ready);
       if (take > 0) {
         if (!alive && rank < take) {
-          const uint32_t* q = pool + (n_ready - 1 - rank);
-#define MCD_LD(w, f) f = __uint_as_float(q[(w) * kPoolSlots]);
-          MCD_POOL_EACH_STATE(MCD_LD)
-#undef MCD_LD
-          rel_id = q[10 * kPoolSlots];
-          ev = q[11 * kPoolSlots];
+          const uint4* q = reinterpret_cast<const uint4*>(pool + (n_ready - 1 - rank) * kSlotWords);
+          pool_unpack(q[0], q[1], q[2], e, rel_id, ev);
           alive = true;
         }
         n_ready -= take;
@@ -399,23 +412,32 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
     float W = 0.f, om = 0.f, uphi = 0.f;
     if (n_pend > 0 && (n_pend >= min(a, kBatchMin) || tail)) {
       // ---- BATCH iteration: current electrons -> ready entries, parked electrons -> lanes, then search ----------
-      // (the two pool regions may overlap, so every word is read by all lanes before it is overwritten; a <= nb
-      // except in the forced batch of the tail, where the pool is nearly empty)
+      // (the two pool regions may overlap: all lanes read their parked entry before any lane stores)
       const int nb = min(n_pend, 32);
       const bool ld = (int)lane < nb;
       // lanes >= nb keep their electron and sit this iteration out (only when fewer than 32 are parked)
       const bool st = alive && (ld || tail);
       const unsigned sm = __ballot_sync(MCD_FULL_MASK, st);
-      const uint32_t* q = pool + (kPoolSlots - n_pend + (int)lane);
-      uint32_t* w = pool + (n_ready + __popc(sm & lt));
-      uint32_t t;
-#define MCD_SWAP(i, f) t = ld ? q[(i) * kPoolSlots] : 0u; __syncwarp(); if (st) w[(i) * kPoolSlots] = __float_as_uint(f); if (ld) f = __uint_as_float(t);
-      MCD_POOL_EACH_STATE(MCD_SWAP)
-#undef MCD_SWAP
-      t = ld ? q[10 * kPoolSlots] : 0u; __syncwarp(); if (st) w[10 * kPoolSlots] = rel_id; if (ld) rel_id = t;
-      t = ld ? q[11 * kPoolSlots] : 0u; __syncwarp(); if (st) w[11 * kPoolSlots] = ev; if (ld) ev = t;
-      const float uz = ld ? __uint_as_float(q[12 * kPoolSlots]) : 0.f;
-      uphi = ld ? __uint_as_float(q[13 * kPoolSlots]) : 0.f;
+      const uint4* q = reinterpret_cast<const uint4*>(pool + (kPoolSlots - n_pend + (int)lane) * kSlotWords);
+      // vector by vector, so that only four temporaries are live: read (all lanes) -> barrier -> store own -> adopt
+      uint4* w = reinterpret_cast<uint4*>(pool + (n_ready + __popc(sm & lt)) * kSlotWords);
+      uint4 t = make_uint4(0u, 0u, 0u, 0u);
+      if (ld) t = q[0];
+      __syncwarp();
+      if (st) w[0] = make_uint4(__float_as_uint(e.E), __float_as_uint(e.x), __float_as_uint(e.y), __float_as_uint(e.z));
+      if (ld) { e.E = __uint_as_float(t.x); e.x = __uint_as_float(t.y); e.y = __uint_as_float(t.z); e.z = __uint_as_float(t.w); }
+      if (ld) t = q[1];
+      __syncwarp();
+      if (st) w[1] = make_uint4(__float_as_uint(e.dx), __float_as_uint(e.dy), __float_as_uint(e.dz), __float_as_uint(e.yx));
+      if (ld) { e.dx = __uint_as_float(t.x); e.dy = __uint_as_float(t.y); e.dz = __uint_as_float(t.z); e.yx = __uint_as_float(t.w); }
+      if (ld) t = q[2];
+      __syncwarp();
+      if (st) w[2] = make_uint4(__float_as_uint(e.yy), __float_as_uint(e.yz), rel_id, ev);
+      if (ld) { e.yy = __uint_as_float(t.x); e.yz = __uint_as_float(t.y); rel_id = t.z; ev = t.w; }
+      uint2 t3 = make_uint2(0u, 0u);
+      if (ld) t3 = *reinterpret_cast<const uint2*>(q + 3);
+      const float uz = __uint_as_float(t3.x);
+      uphi = __uint_as_float(t3.y);
       n_ready += __popc(sm);
       n_pend -= nb;
       alive = ld || (alive && !st);
@@ -458,14 +480,9 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
         const int r = __popc(pm & lt);
         if (park) {
           if (r < room) {
-            uint32_t* w = pool + (kPoolSlots - n_pend - 1 - r);
-#define MCD_ST(i, f) w[(i) * kPoolSlots] = __float_as_uint(f);
-            MCD_POOL_EACH_STATE(MCD_ST)
-#undef MCD_ST
-            w[10 * kPoolSlots] = rel_id;
-            w[11 * kPoolSlots] = ev | ((uint32_t)slot << 24) | ((uint32_t)(outcome + 1) << 28) | ((uint32_t)(flags & 1) << 31);
-            w[12 * kPoolSlots] = __float_as_uint(uz);
-            w[13 * kPoolSlots] = __float_as_uint(uphi);
+            uint32_t* w = pool + (kPoolSlots - n_pend - 1 - r) * kSlotWords;
+            pool_put(w, e, rel_id, ev | ((uint32_t)slot << 24) | ((uint32_t)(outcome + 1) << 28) | ((uint32_t)(flags & 1) << 31));
+            *reinterpret_cast<uint2*>(w + 12) = make_uint2(__float_as_uint(uz), __float_as_uint(uphi));
             alive = false;
             outcome = -1;
           } else {

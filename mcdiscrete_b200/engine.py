@@ -378,28 +378,35 @@ class Engine:
         els, scats = self.drain(first_id, count, pinned=pinned, stream=stream, ordered=ordered) if drain else (None, {})
         return RunResult(first_id, count, els, scats, cnt, self.kernel_ms())
 
-    def run_batches(self, total, batch, first_id=0, max_scat_rows=None, on_launched=None, ordered=False):
-        """Simulate `total` electrons in batches of `batch`, PIPELINED over two contexts / two CUDA streams:
-        while the host drains batch k (D2H into pinned buffers) batch k+1 already runs, and its blocks fill the
-        SMs that the tail of batch k leaves idle.  Yields one RunResult per batch, in order.  Rows of a yielded
-        result live in reused pinned buffers: consume them before advancing the generator twice.
+    def run_batches(self, total, batch, first_id=0, max_scat_rows=None, on_launched=None, ordered=False, depth=None):
+        """Simulate `total` electrons in batches of `batch`, PIPELINED over `depth` contexts / CUDA streams
+        (default 4 for statistics-only runs, 2 when scats rows are recorded): while the host drains batch k
+        (D2H into pinned buffers) the next batches already run, their blocks fill the SMs that the tail of batch k
+        leaves idle, and the tail hand-over passes of one batch hide behind the main pass of another.  Yields
+        one RunResult per batch, in order.  Rows of a yielded result live in reused pinned buffers: consume them
+        before advancing the generator `depth` times.
         `on_launched(engine, torch_stream)` is called right after each launch (e.g. to enqueue the NCCL
         all-reduce of engine.stats_tensor() on that stream)."""
         import torch
+        from collections import deque
         if self.params.mode == _lib.MODE_DS and self.tables is None:
             from .probTables import genTables
             genTables(self.inputPar, engine=self)
-        # the second context, its device buffers, the pinned staging buffers and the two streams are kept for
+        depth = int(depth or (2 if self.row_words else 4))
+        # the extra contexts, their device buffers, the pinned staging buffers and the streams are kept for
         # later calls (creating them costs tens of milliseconds of cudaMalloc / page-locking)
         pipe = getattr(self, '_pipe', None)
         if pipe is None:
-            pipe = self._pipe = (self.clone(), [torch.cuda.Stream(device=self.device),
-                                                torch.cuda.Stream(device=self.device)])
-        engs = [self, pipe[0]]
-        streams = pipe[1]
+            pipe = self._pipe = ([], [])
+        while len(pipe[0]) < depth - 1:
+            pipe[0].append(self.clone())
+        while len(pipe[1]) < depth:
+            pipe[1].append(torch.cuda.Stream(device=self.device))
+        engs = [self] + pipe[0][:depth - 1]
+        streams = pipe[1][:depth]
         if max_scat_rows is None:
             max_scat_rows = (batch * min(int(self.inputPar['maxScatt']), 512) + 65536) if self.row_words else 0
-        pending = None
+        pending = deque()
 
         def finish(p):
             e, st, first, cnt = p
@@ -413,19 +420,19 @@ class Engine:
         try:
             for first in range(first_id, first_id + total, batch):
                 cnt = min(batch, first_id + total - first)
-                e, st = engs[k % 2], streams[k % 2].cuda_stream
+                e, st = engs[k % depth], streams[k % depth].cuda_stream
                 e.set_capacity(max(batch, e.cap_el), max(max_scat_rows, e.cap_sc))
                 e.reset_stats(st)
                 e.launch(first, cnt, st)
                 if on_launched is not None:
-                    with torch.cuda.stream(streams[k % 2]):
-                        on_launched(e, streams[k % 2])
-                if pending is not None:
-                    yield finish(pending)
-                pending = (e, st, first, cnt)
+                    with torch.cuda.stream(streams[k % depth]):
+                        on_launched(e, streams[k % depth])
+                pending.append((e, st, first, cnt))
+                if len(pending) == depth:                  # every context is busy: drain the oldest batch
+                    yield finish(pending.popleft())
                 k += 1
-            if pending is not None:
-                yield finish(pending)
+            while pending:
+                yield finish(pending.popleft())
             self.next_id = max(self.next_id, first_id + total)
         finally:
             for st in streams:

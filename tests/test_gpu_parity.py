@@ -483,6 +483,57 @@ def test_pipelined_batches_equal_single_run():
     eng.close()
 
 
+@pytest.mark.parametrize('kw,n', [
+    (dict(Emin=10000.), 60000),                                  # Si, S = 3
+    (dict(Emin=10000.), 37),                                     # less than two warps of work
+    (dict(material='Cu', Emin=10000.), 30000),                   # S = 4
+    (dict(material='Au', E0=30000., Emin=15000., s_tilt=0., maxScatt=10000), 12000),     # S = 8, long trajectories
+    (dict(Emin=10000., maxScatt=40), 20000),                     # mostly 'long' outcomes
+    (dict(s_tilt=89.5, Emin=19985.), 20000),                     # bks -> abs double records (Q4)
+    (dict(Emin=10000., thickness=2000.), 20000),                 # thin film: transmission
+])
+def test_statistics_only_kernel_equals_row_recording_kernel(kw, n):
+    """Statistics-only DS runs go through traj_kernel_pool (table events parked in a warp-private pool and searched
+    32 at a time; warps that run dry hand their last electrons to follow-up launches); runs that record scats rows go
+    through traj_kernel (every event completed in its own iteration).  Uniforms are a function of (seed, electron
+    id, event), so both must produce the same els rows, histograms and counters, bit for bit."""
+    from mcdiscrete_b200.probTables import genTables
+    res = []
+    for scat in ([], ['type']):
+        ip = base_input(scatter_output=scat, **kw)
+        eng = make_engine(scatter_output=scat, **kw)
+        genTables(ip, engine=eng)
+        r = eng.run(count=n, first_id=5000)
+        h = eng.histograms()
+        res.append((r.els.copy(), {k: v[0].copy() for k, v in h.items()}, r.counters, eng.launch_info()))
+        eng.close()
+    (els_a, h_a, c_a, li_a), (els_b, h_b, c_b, li_b) = res
+    assert li_a['launches_per_run'] > 1 and li_b['launches_per_run'] == 1      # hand-over passes vs single launch
+    assert np.array_equal(els_a, els_b)
+    for k in h_a:
+        assert np.array_equal(h_a[k], h_b[k]), k
+    for k in ('electrons_done', 'events', 'double_records', 'nan_clamped', 'select_exact', 'outcome'):
+        assert c_a[k] == c_b[k], k
+    assert c_a['electrons_done'] == n
+
+
+def test_pipelined_statistics_only_batches():
+    """run_batches at its default depth (4 contexts / streams) for a statistics-only run: every batch complete, rows
+    equal to one big run."""
+    from mcdiscrete_b200.probTables import genTables
+    ip = base_input(scatter_output=[], Emin=10000.)
+    eng = make_engine(scatter_output=[], Emin=10000.)
+    genTables(ip, engine=eng)
+    N = 90000
+    whole = eng.run(count=N, first_id=0).els.copy()
+    parts = []
+    for r in eng.run_batches(N, 10000, first_id=0):
+        assert r.counters['electrons_done'] == r.count == 10000
+        parts.append(r.els.copy())
+    assert len(parts) == 9 and np.array_equal(np.concatenate(parts), whole)
+    eng.close()
+
+
 def test_device_regrouping_of_scats_rows():
     """mcd_order_scats: rows regrouped on the device into the reference's order == host lexsort of the appended rows."""
     eng = make_engine(Emin=15000.)
