@@ -42,6 +42,8 @@ struct mcd_ctx {
   size_t l2_persist_bytes = 0;                // persisting-L2 carve-out (0 = not used)
   float4* sig_poly = nullptr;                 // per-cell quadratics of the cumulative cross-sections
   double sig_poly_err = 0.0;                  // verified max error relative to the total
+  float4* sig_hot = nullptr;                  // hot records (Ruth / Ruth+Quinn boundaries, total) on a finer grid
+  double sig_hot_err = 0.0;                   // verified max error of the two linear boundaries
   int slot_order[MCD_MAX_SHELLS] = {0};
   // outputs
   mcd_el_row* els = nullptr;
@@ -212,6 +214,80 @@ int build_sig_poly(mcd_ctx* c, const int* order) {
       P.sig_ncell = ncell;
       P.sig_nch = nch;
       c->sig_poly_err = worst;
+      return 1;
+    }
+  }
+  return 0;
+}
+
+// Hot records (DevParams::sig_hot): per cell of a finer grid, linear interpolants of the Ruth and Ruth+Quinn
+// boundaries (Chebyshev nodes of [0,1], verified <= 1.5e-6 of the total on 7 further points) and the quadratic of
+// the total (verified <= 1.5e-7); the grid is refined until both hold.
+int build_sig_hot(mcd_ctx* c, const int* order) {
+  const mcd_params& p = c->par;
+  const mcd_material& mt = c->mat;
+  const int nch = mt.n_shells + 3;
+  int e_min, e_max;
+  frexp(p.Emin * 0.999, &e_min); e_min -= 1;
+  frexp(p.E0, &e_max); e_max -= 1;
+  if (e_min < 1 || e_max > 30) return 0;
+  const double n2[2] = {0.5 - 0.25 * sqrt(2.0), 0.5 + 0.25 * sqrt(2.0)};
+  const double n3[3] = {0.5 - 0.25 * sqrt(3.0), 0.5, 0.5 + 0.25 * sqrt(3.0)};
+  for (int logM = 7; logM <= 13; ++logM) {
+    const int M = 1 << logM;
+    const int ncell = (e_max - e_min + 1) * M;
+    std::vector<float4> hot((size_t)ncell * 2);
+    double worst_lin = 0.0, worst_tot = 0.0;
+    for (int cell = 0; cell < ncell; ++cell) {
+      const double Ea = ldexp(1.0 + (double)(cell % M) / M, e_min + cell / M);
+      const double dEc = ldexp(1.0 / M, e_min + cell / M);
+      const double Elo = mt.plasmon_e * 1.001;
+      if (Ea + dEc <= Elo) {                                   // below the Quinn threshold: never visited
+        hot[2 * (size_t)cell] = make_float4(0.5f, 0.f, 0.75f, 0.f);
+        hot[2 * (size_t)cell + 1] = make_float4(1.f, 0.f, 0.f, 0.f);
+        continue;
+      }
+      double f2[2][MCD_MAX_CHANNELS], f3[3][MCD_MAX_CHANNELS];
+      for (int i = 0; i < 2; ++i) cum_host(p, mt, order, fmax(Ea + n2[i] * dEc, Elo), f2[i]);
+      for (int i = 0; i < 3; ++i) cum_host(p, mt, order, fmax(Ea + n3[i] * dEc, Elo), f3[i]);
+      float lin[2][2];
+      for (int k = 0; k < 2; ++k) {
+        const double c1 = (f2[1][k] - f2[0][k]) / (n2[1] - n2[0]);
+        lin[k][0] = (float)(f2[0][k] - c1 * n2[0]);
+        lin[k][1] = (float)c1;
+      }
+      const int T = nch - 1;
+      const double d01 = (f3[1][T] - f3[0][T]) / (n3[1] - n3[0]);
+      const double d12 = (f3[2][T] - f3[1][T]) / (n3[2] - n3[1]);
+      const double q2 = (d12 - d01) / (n3[2] - n3[0]);
+      const double q1 = d01 - q2 * (n3[0] + n3[1]);
+      const double q0 = f3[0][T] - n3[0] * (d01 - q2 * n3[1]);
+      hot[2 * (size_t)cell] = make_float4(lin[0][0], lin[0][1], lin[1][0], lin[1][1]);
+      hot[2 * (size_t)cell + 1] = make_float4((float)q0, (float)q1, (float)q2, 0.f);
+      if (Ea + dEc < p.Emin * 0.999 || Ea > p.E0 * 1.001) continue;       // outside the visited range
+      for (int j = 0; j < 7; ++j) {
+        const double x = (j + 0.5) / 7.0;
+        const double E = Ea + x * dEc;
+        if (E <= Elo) continue;
+        double ref[MCD_MAX_CHANNELS];
+        cum_host(p, mt, order, E, ref);
+        const float xf = (float)x;
+        for (int k = 0; k < 2; ++k)
+          worst_lin = fmax(worst_lin, fabs((double)fmaf(lin[k][1], xf, lin[k][0]) - ref[k]) / ref[T]);
+        worst_tot = fmax(worst_tot, fabs((double)fmaf(fmaf((float)q2, xf, (float)q1), xf, (float)q0) - ref[T]) / ref[T]);
+      }
+    }
+    if (worst_lin < 1.5e-6 && worst_tot < 1.5e-7) {
+      cudaFree(c->sig_hot); c->sig_hot = nullptr;
+      if (cudaMalloc(&c->sig_hot, hot.size() * sizeof(float4)) != cudaSuccess) return 0;
+      if (cudaMemcpy(c->sig_hot, hot.data(), hot.size() * sizeof(float4), cudaMemcpyHostToDevice) != cudaSuccess) return 0;
+      DevParams& P = c->P;
+      P.sig_hot = c->sig_hot;
+      P.hot_shift = 23 - logM;
+      P.hot_base = (uint32_t)(((uint32_t)(e_min + 127) << 23) >> P.hot_shift);
+      P.hot_ncell = ncell;
+      c->sig_hot_err = worst_lin;
+      if (worst_tot > c->sig_poly_err) c->sig_poly_err = worst_tot;
       return 1;
     }
   }
@@ -467,7 +543,7 @@ int mcd_create(const mcd_params* p, const mcd_material* m, int device, mcd_ctx**
   build_dev_params(c);
   c->P.use_sig_poly = 0;
   if (p->mode == MCD_MODE_DS && c->P.order_static && !getenv("MCD_NO_SIGPOLY"))
-    c->P.use_sig_poly = build_sig_poly(c, c->slot_order);
+    c->P.use_sig_poly = build_sig_poly(c, c->slot_order) && build_sig_hot(c, c->slot_order);
   mcd_scat_layout L;
   layout_of(p->scat_mask, &L);
   c->P.scat_row_words = (int)L.row_words;
@@ -526,7 +602,7 @@ int mcd_destroy(mcd_ctx* c) {
   if (!c) return MCD_OK;
   cudaSetDevice(c->device);
   if (c->owns_tables) for (auto& t : c->tab) free_table(t);
-  if (c->owns_tables) cudaFree(c->sig_poly);
+  if (c->owns_tables) { cudaFree(c->sig_poly); cudaFree(c->sig_hot); }
   cudaFree(c->els); cudaFree(c->scats); cudaFree(c->chunk_next); cudaFree(c->chunk_count); cudaFree(c->ticket);
   cudaFree(c->rq[0]); cudaFree(c->rq[1]);
   cudaFree(c->nev); cudaFree(c->sorted); cudaFree(c->offsets); cudaFree(c->tile_tmp); cudaFree(c->total_dev);

@@ -178,8 +178,9 @@ traj_kernel(const __grid_constant__ DevParams P, const DevOut O, const unsigned 
       const float4 u = event_uniforms(P, first_id + rel_id, ev);
       if (MODE == MCD_MODE_DS) {
         EventMid mid;
-        ds_phase_a<S>(P, e, u, row, mid);
-        ds_phase_b(P, e, u, row, mid);
+        float tot;
+        ds_phase_a<S>(P, e, u, row, mid, tot);
+        ds_phase_b<S>(P, e, u, row, mid, tot);
       } else {
         cont_event(P, e, u, row);
       }
@@ -275,16 +276,32 @@ constexpr int kPoolSlots = MCD_POOL_SLOTS;
 #define MCD_BATCH_MIN 32             // parked electrons that trigger a batch iteration (<= 32)
 #endif
 constexpr int kBatchMin = MCD_BATCH_MIN;
-constexpr int kSlotWords = 20;       // 14 used: E x y z | dx dy dz yx | yy yz rel_id ev+bits | u.z u.w; a stride of 20
+constexpr int kSlotWords = 20;       // 16 used: E x y z | dx dy dz yx | yy yz rel_id ev+bits | u.z u.w u.x total; a stride of 20
                                      // words keeps the 128-bit accesses of 8 consecutive slots on distinct banks
 
-// out-of-line copy of the table search for the pool-full case (keeps the hot loop's code small)
-static __device__ __noinline__ float2 table_loss_call(const DevParams& P, float E, int tab, float uz, int* flags) {
+// a parked event (table channel): resolve which one (ds_cold_slot), search its table, binary-collision angle
+template <int S>
+__device__ __forceinline__ void ds_table_event(const DevParams& P, const ElState& e, float ux, float tot, float uz,
+                                               int& slot, int& flags, float& W, float& om) {
+  if (slot == MCD_SLOT_UNRESOLVED) slot = ds_cold_slot<S>(P, e.E, ux, tot, flags);
+  if (slot >= 2) {
+    ds_table_loss(P, e, slot_table<S>(P, slot), uz, flags, W, om);
+  } else {                                                   // the exact path moved it back to Ruth / Quinn (rare)
+    W = (slot == 1) ? P.m.Epl : 0.0f;
+    om = (slot == 0) ? ruth_om(P.m, f_rcp(e.E), uz) : 0.0f;
+  }
+}
+
+// out-of-line copy for the pool-full case (keeps the hot loop's code small); returns (W, om)
+template <int S>
+static __device__ __noinline__ float2 table_event_call(const DevParams& P, float E, float ux, float tot, float uz,
+                                                       int* slot, int* flags) {
   ElState t;
   t.E = E;
   float W, om;
-  int f = *flags;
-  ds_table_loss(P, t, tab, uz, f, W, om);
+  int sl = *slot, f = *flags;
+  ds_table_event<S>(P, t, ux, tot, uz, sl, f, W, om);
+  *slot = sl;
   *flags = f;
   return make_float2(W, om);
 }
@@ -434,10 +451,8 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
       __syncwarp();
       if (st) w[2] = make_uint4(__float_as_uint(e.yy), __float_as_uint(e.yz), rel_id, ev);
       if (ld) { e.yy = __uint_as_float(t.x); e.yz = __uint_as_float(t.y); rel_id = t.z; ev = t.w; }
-      uint2 t3 = make_uint2(0u, 0u);
-      if (ld) t3 = *reinterpret_cast<const uint2*>(q + 3);
-      const float uz = __uint_as_float(t3.x);
-      uphi = __uint_as_float(t3.y);
+      if (ld) t = q[3];                                          // u.z, u.w, u.x, total of the parked event
+      uphi = __uint_as_float(t.y);
       n_ready += __popc(sm);
       n_pend -= nb;
       alive = ld || (alive && !st);
@@ -447,9 +462,7 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
         outcome = (int)((ev >> 28) & 7u) - 1;
         flags = (int)(ev >> 31);                   // MCD_EVF_EXACT = 1
         ev &= 0xffffffu;
-        int tab = MCD_TABLE_MOLLER;
-        if (slot >= 3) tab = P.gryz_per_shell ? (MCD_TABLE_GRYZ0 + (S - 1 - P.m.gShell[slot - 3])) : MCD_TABLE_GRYZ0;
-        ds_table_loss(P, e, tab, uz, flags, W, om);
+        ds_table_event<S>(P, e, __uint_as_float(t.z), __uint_as_float(t.w), __uint_as_float(t.x), slot, flags, W, om);
         done = true;
       }
     } else {
@@ -458,12 +471,12 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
       const bool has_row = alive && (ev < (uint32_t)P.maxScatt);
       if (alive && !has_row) outcome = MCD_OUT_LONG;
       bool park = false;
-      float uz = 0.f;
+      float uz = 0.f, ux = 0.f, tot = 0.f;
       EventRow row;
       if (has_row) {
         const float4 u = event_uniforms(P, first_id + rel_id, ev);
         EventMid mid;
-        ds_phase_a<S>(P, e, u, row, mid);
+        ds_phase_a<S>(P, e, u, row, mid, tot);
         outcome = row.outcome;
         slot = row.slot;
         flags = row.flags;
@@ -471,6 +484,7 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
         W = mid.W;
         om = mid.om;
         uz = u.z;
+        ux = u.x;
         park = mid.tab >= 0;
         done = !park;
       }
@@ -482,14 +496,12 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
           if (r < room) {
             uint32_t* w = pool + (kPoolSlots - n_pend - 1 - r) * kSlotWords;
             pool_put(w, e, rel_id, ev | ((uint32_t)slot << 24) | ((uint32_t)(outcome + 1) << 28) | ((uint32_t)(flags & 1) << 31));
-            *reinterpret_cast<uint2*>(w + 12) = make_uint2(__float_as_uint(uz), __float_as_uint(uphi));
+            *reinterpret_cast<uint4*>(w + 12) = make_uint4(__float_as_uint(uz), __float_as_uint(uphi), __float_as_uint(ux), __float_as_uint(tot));
             alive = false;
             outcome = -1;
           } else {
             // pool full (rare): this lane searches its table at once, like traj_kernel does for every table event
-            int tab = MCD_TABLE_MOLLER;
-            if (slot >= 3) tab = P.gryz_per_shell ? (MCD_TABLE_GRYZ0 + (S - 1 - P.m.gShell[slot - 3])) : MCD_TABLE_GRYZ0;
-            const float2 r2 = table_loss_call(P, e.E, tab, uz, &flags);
+            const float2 r2 = table_event_call<S>(P, e.E, ux, tot, uz, &slot, &flags);
             W = r2.x;
             om = r2.y;
             done = true;

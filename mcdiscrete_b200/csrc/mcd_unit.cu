@@ -52,10 +52,17 @@ __global__ void k_cum(const __grid_constant__ DevParams P, const float* E, uint6
     const uint32_t cell = min((bits >> P.sig_shift) - P.sig_base, (uint32_t)(P.sig_ncell - 1));
     const float x = (float)(bits & ((1u << P.sig_shift) - 1u)) * __uint_as_float((uint32_t)(127 - P.sig_shift) << 23);
     const float4* q = P.sig_poly + (size_t)cell * (size_t)nch;
-    for (int k = 0; k < nch; ++k) {
+    for (int k = 2; k < nch - 1; ++k) {                    // the boundaries ds_cold_slot reads
       const float4 c = __ldg(q + k);
       cum_out[i * nch + k] = fmaf(fmaf(c.z, x, c.y), x, c.x);
     }
+    // the hot record: Ruth and Ruth+Quinn boundaries (linear) and the total (quadratic), finer cells
+    const uint32_t hc = min((bits >> P.hot_shift) - P.hot_base, (uint32_t)(P.hot_ncell - 1));
+    const float hx = (float)(bits & ((1u << P.hot_shift) - 1u)) * __uint_as_float((uint32_t)(127 - P.hot_shift) << 23);
+    const float4 h0 = __ldg(P.sig_hot + 2 * (size_t)hc), h1 = __ldg(P.sig_hot + 2 * (size_t)hc + 1);
+    cum_out[i * nch + 0] = fmaf(h0.y, hx, h0.x);
+    cum_out[i * nch + 1] = fmaf(h0.w, hx, h0.z);
+    cum_out[i * nch + nch - 1] = fmaf(fmaf(h1.z, hx, h1.y), hx, h1.x);
   } else {
     const DevMat& m = P.m;
     const float invE = f_rcp(e);
@@ -159,8 +166,9 @@ __device__ void step_one(const DevParams& P, bool on, ElState& e, float4 u, Even
   if (!on) return;
   if (P.mode == MCD_MODE_DS) {
     EventMid mid;
-    ds_phase_a<S>(P, e, u, row, mid);
-    ds_phase_b(P, e, u, row, mid);
+    float tot;
+    ds_phase_a<S>(P, e, u, row, mid, tot);
+    ds_phase_b<S>(P, e, u, row, mid, tot);
   } else {
     cont_event(P, e, u, row);
   }

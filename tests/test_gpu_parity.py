@@ -564,8 +564,10 @@ def test_device_regrouping_of_scats_rows():
 @pytest.mark.parametrize('name,E0,Emin', [('Si', 20000., 10000.), ('Cu', 20000., 10000.), ('Au', 30000., 15000.),
                                           ('Al', 30000., 2600.)])
 def test_cumulative_cross_sections_of_the_hot_path(name, E0, Emin):
-    """The cumulative inverse mean free paths the trajectory kernel uses (per-cell quadratics built and verified at
-    mcd_create) against the float64 formulas: every boundary within 3e-7 of the total."""
+    """The cumulative inverse mean free paths the trajectory kernel uses (built and verified at mcd_create) against
+    the float64 formulas.  The total (it sets the path length) and the table-channel boundaries are per-cell
+    quadratics, within 3e-7 of the total; the Ruth and Ruth+Quinn boundaries, which only feed the channel pick and
+    its 1e-5 guard band, are per-cell linear interpolants, within 2e-6 of the total."""
     eng = make_engine(material=name, E0=E0, Emin=Emin)
     m = o.Material(name)
     rng = np.random.default_rng(9)
@@ -575,6 +577,8 @@ def test_cumulative_cross_sections_of_the_hot_path(name, E0, Emin):
     assert slot_ch[0] == 0 and slot_ch[1] == len(m.Es) + 2 and slot_ch[2] == 1
     scale = m.atnd * 1e-14
     ref = np.array([np.cumsum(np.array(o.sigmas_ds(float(e), m, 10.))[slot_ch]) * scale for e in E])
-    assert (np.abs(cum - ref) / ref[:, -1:]).max() < 3e-7
+    rel = np.abs(cum - ref) / ref[:, -1:]
+    assert rel[:, 2:].max() < 3e-7
+    assert rel[:, :2].max() < 2e-6
     assert (np.diff(cum, axis=1) >= 0).all()
     eng.close()
