@@ -32,7 +32,8 @@ constexpr int kCntDouble = 7;
 constexpr int kCntNan = 8;
 constexpr int kCntExact = 9;
 constexpr int kCntChan = 10;         // MCD_MAX_CHANNELS
-constexpr int kCntTotal = kCntChan + MCD_MAX_CHANNELS;
+constexpr int kCntEventsHi = kCntChan + MCD_MAX_CHANNELS;      // carry word of the event count
+constexpr int kCntTotal = kCntEventsHi + 1;
 
 __device__ __forceinline__ unsigned lanemask_lt() {
   unsigned m;
@@ -63,15 +64,17 @@ __device__ __forceinline__ void store_scat_row(uint32_t* __restrict__ dst, uint3
 // 16-byte stores), outcome / event counters and, for 'bks', the fused backscatter histograms.  preE = energy before
 // the event's loss; e = direction before the event's rotation, position as update_xyz left it.
 __device__ __forceinline__ void retire_lane(const DevParams& P, const DevOut& O, unsigned int* s_hist,
-                                            unsigned long long* s_cnt, bool want_hist, int outcome, bool dbl,
+                                            unsigned int* s_cnt, bool want_hist, int outcome, bool dbl,
                                             float preE, const ElState& e, uint32_t rel_id, uint32_t nev) {
   float4* dst = reinterpret_cast<float4*>(O.els + rel_id);
   dst[0] = make_float4(__uint_as_float((uint32_t)outcome | (dbl ? 0x100u : 0u)), preE, e.dx, e.dy);
   dst[1] = make_float4(e.dz, e.x, e.y, e.z);
-  atomicAdd(&s_cnt[kCntOutcome + outcome], 1ull);
-  atomicAdd(&s_cnt[kCntDone], 1ull);
-  atomicAdd(&s_cnt[kCntEvents], (unsigned long long)nev);
-  if (dbl) atomicAdd(&s_cnt[kCntDouble], 1ull);
+  // block counters are 32-bit words (native shared-memory atomics; a 64-bit shared atomicAdd is a CAS loop); the
+  // event count carries into a second word
+  atomicAdd(&s_cnt[kCntOutcome + outcome], 1u);
+  atomicAdd(&s_cnt[kCntDone], 1u);
+  if (atomicAdd(&s_cnt[kCntEvents], nev) + nev < nev) atomicAdd(&s_cnt[kCntEventsHi], 1u);
+  if (dbl) atomicAdd(&s_cnt[kCntDouble], 1u);
   if (want_hist && outcome == MCD_OUT_BKS) {
     int b = (int)((preE - P.hist.e_lo) * P.hist.e_scale);
     b = max(0, min(b, MCD_HIST_E_BINS - 1));
@@ -89,7 +92,7 @@ __device__ __forceinline__ void retire_lane(const DevParams& P, const DevOut& O,
 
 // block statistics -> global stats block (histograms || mcd_counters), once per block
 __device__ __forceinline__ void flush_block_stats(const DevOut& O, const unsigned int* s_hist,
-                                                  const unsigned long long* s_cnt, const unsigned long long* s_rows,
+                                                  const unsigned int* s_cnt, const unsigned long long* s_rows,
                                                   bool want_scats, bool want_chan) {
   for (int i = threadIdx.x; i < MCD_HIST_TOTAL; i += kThreads) {
     const unsigned int v = s_hist[i];
@@ -98,19 +101,19 @@ __device__ __forceinline__ void flush_block_stats(const DevOut& O, const unsigne
   unsigned long long* cnt = O.stats + MCD_HIST_TOTAL;
   // mcd_counters layout: electrons_done, events, outcome[5], double_records, stored, dropped, nan, exact, channel[]
   if (threadIdx.x == 0) {
-    atomicAdd(cnt + 0, s_cnt[kCntDone]);
-    atomicAdd(cnt + 1, s_cnt[kCntEvents]);
-    for (int i = 0; i < 5; ++i) if (s_cnt[kCntOutcome + i]) atomicAdd(cnt + 2 + i, s_cnt[kCntOutcome + i]);
-    if (s_cnt[kCntDouble]) atomicAdd(cnt + 7, s_cnt[kCntDouble]);
+    atomicAdd(cnt + 0, (unsigned long long)s_cnt[kCntDone]);
+    atomicAdd(cnt + 1, ((unsigned long long)s_cnt[kCntEventsHi] << 32) | s_cnt[kCntEvents]);
+    for (int i = 0; i < 5; ++i) if (s_cnt[kCntOutcome + i]) atomicAdd(cnt + 2 + i, (unsigned long long)s_cnt[kCntOutcome + i]);
+    if (s_cnt[kCntDouble]) atomicAdd(cnt + 7, (unsigned long long)s_cnt[kCntDouble]);
     if (want_scats) {
       if (s_rows[0]) atomicAdd(cnt + 8, s_rows[0]);
       if (s_rows[1]) atomicAdd(cnt + 9, s_rows[1]);
     }
-    if (s_cnt[kCntNan]) atomicAdd(cnt + 10, s_cnt[kCntNan]);
-    if (s_cnt[kCntExact]) atomicAdd(cnt + 11, s_cnt[kCntExact]);
+    if (s_cnt[kCntNan]) atomicAdd(cnt + 10, (unsigned long long)s_cnt[kCntNan]);
+    if (s_cnt[kCntExact]) atomicAdd(cnt + 11, (unsigned long long)s_cnt[kCntExact]);
     if (want_chan)
       for (int i = 0; i < MCD_MAX_CHANNELS; ++i)
-        if (s_cnt[kCntChan + i]) atomicAdd(cnt + 12 + i, s_cnt[kCntChan + i]);
+        if (s_cnt[kCntChan + i]) atomicAdd(cnt + 12 + i, (unsigned long long)s_cnt[kCntChan + i]);
   }
 }
 
@@ -119,11 +122,11 @@ __global__ void __launch_bounds__(kThreads, MCD_MIN_BLOCKS)
 traj_kernel(const __grid_constant__ DevParams P, const DevOut O, const unsigned long long first_id,
             const unsigned long long count) {
   __shared__ unsigned int s_hist[MCD_HIST_TOTAL];
-  __shared__ unsigned long long s_cnt[kCntTotal];
+  __shared__ unsigned int s_cnt[kCntTotal];
   __shared__ unsigned long long s_rows[2];      // stored, dropped
 
   for (int i = threadIdx.x; i < MCD_HIST_TOTAL; i += kThreads) s_hist[i] = 0u;
-  for (int i = threadIdx.x; i < kCntTotal; i += kThreads) s_cnt[i] = 0ull;
+  for (int i = threadIdx.x; i < kCntTotal; i += kThreads) s_cnt[i] = 0u;
   if (threadIdx.x < 2) s_rows[threadIdx.x] = 0ull;
   __syncthreads();
 
@@ -232,10 +235,10 @@ traj_kernel(const __grid_constant__ DevParams P, const DevOut O, const unsigned 
       }
     }
     if (has_row) {
-      if (want_chan) atomicAdd(&s_cnt[kCntChan + slot_channel(P.m, row.slot)], 1ull);
+      if (want_chan) atomicAdd(&s_cnt[kCntChan + slot_channel(P.m, row.slot)], 1u);
       if (row.flags & (MCD_EVF_NANCLAMP | MCD_EVF_EXACT)) {
-        if (row.flags & MCD_EVF_NANCLAMP) atomicAdd(&s_cnt[kCntNan], 1ull);
-        if (row.flags & MCD_EVF_EXACT) atomicAdd(&s_cnt[kCntExact], 1ull);
+        if (row.flags & MCD_EVF_NANCLAMP) atomicAdd(&s_cnt[kCntNan], 1u);
+        if (row.flags & MCD_EVF_EXACT) atomicAdd(&s_cnt[kCntExact], 1u);
       }
       ++ev;
     }
@@ -292,18 +295,16 @@ __device__ __forceinline__ void ds_table_event(const DevParams& P, const ElState
   }
 }
 
-// out-of-line copy for the pool-full case (keeps the hot loop's code small); returns (W, om)
+// out-of-line copy for the pool-full case (keeps the hot loop's code small); everything travels by value so that
+// the caller's slot / flags stay in registers: returns (W, om, slot, flags)
 template <int S>
-static __device__ __noinline__ float2 table_event_call(const DevParams& P, float E, float ux, float tot, float uz,
-                                                       int* slot, int* flags) {
+static __device__ __noinline__ float4 table_event_call(const DevParams& P, float E, float ux, float tot, float uz,
+                                                       int slot, int flags) {
   ElState t;
   t.E = E;
   float W, om;
-  int sl = *slot, f = *flags;
-  ds_table_event<S>(P, t, ux, tot, uz, sl, f, W, om);
-  *slot = sl;
-  *flags = f;
-  return make_float2(W, om);
+  ds_table_event<S>(P, t, ux, tot, uz, slot, flags, W, om);
+  return make_float4(W, om, __int_as_float(slot), __int_as_float(flags));
 }
 
 __device__ __forceinline__ void pool_put(uint32_t* slot, const ElState& e, uint32_t rel_id, uint32_t evw) {
@@ -334,11 +335,11 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
   const unsigned long long count = RESUME ? *O.rq_in_count : count_arg;
   if (RESUME && (unsigned long long)blockIdx.x * (2ull * kThreads) >= count) return;
   __shared__ unsigned int s_hist[MCD_HIST_TOTAL];
-  __shared__ unsigned long long s_cnt[kCntTotal];
+  __shared__ unsigned int s_cnt[kCntTotal];
   __shared__ __align__(16) uint32_t s_pool[kThreads / 32][kSlotWords * kPoolSlots];
 
   for (int i = threadIdx.x; i < MCD_HIST_TOTAL; i += kThreads) s_hist[i] = 0u;
-  for (int i = threadIdx.x; i < kCntTotal; i += kThreads) s_cnt[i] = 0ull;
+  for (int i = threadIdx.x; i < kCntTotal; i += kThreads) s_cnt[i] = 0u;
   __syncthreads();
 
   const unsigned lane = threadIdx.x & 31u;
@@ -346,8 +347,12 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
   const bool want_hist = (P.flags & MCD_FLAG_HISTOGRAMS) != 0u;
   const bool want_chan = (P.flags & MCD_FLAG_CHANNEL_COUNTS) != 0u;
   uint32_t* const pool = s_pool[threadIdx.x >> 5];
-  int n_ready = 0, n_pend = 0;                   // warp-uniform
-  bool exhausted = false;                        // warp-uniform: the ticket ran past `count`
+  // warp-uniform bookkeeping in ONE register (the loop is at the register limit of 6 blocks per SM):
+  // bits 0-7 ready entries, bits 8-15 parked entries, bit 16 = the ticket ran past `count`
+  uint32_t wst = 0u;
+#define n_ready ((int)(wst & 0xffu))
+#define n_pend ((int)((wst >> 8) & 0xffu))
+#define exhausted ((wst >> 16) != 0u)
 
   bool alive = false;
   ElState e;
@@ -366,7 +371,7 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
           pool_unpack(q[0], q[1], q[2], e, rel_id, ev);
           alive = true;
         }
-        n_ready -= take;
+        wst -= (uint32_t)take;
       }
       const int nreq = nneed - take;
       if (nreq > 0 && !exhausted) {
@@ -396,7 +401,7 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
             }
           }
         }
-        exhausted = (base + (unsigned long long)nreq >= count);
+        if (base + (unsigned long long)nreq >= count) wst |= 0x10000u;
       }
     }
     const unsigned am = __ballot_sync(MCD_FULL_MASK, alive);
@@ -453,8 +458,7 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
       if (ld) { e.yy = __uint_as_float(t.x); e.yz = __uint_as_float(t.y); rel_id = t.z; ev = t.w; }
       if (ld) t = q[3];                                          // u.z, u.w, u.x, total of the parked event
       uphi = __uint_as_float(t.y);
-      n_ready += __popc(sm);
-      n_pend -= nb;
+      wst += (uint32_t)__popc(sm) - ((uint32_t)nb << 8);
       alive = ld || (alive && !st);
       __syncwarp();
       if (ld) {
@@ -501,13 +505,15 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
             outcome = -1;
           } else {
             // pool full (rare): this lane searches its table at once, like traj_kernel does for every table event
-            const float2 r2 = table_event_call<S>(P, e.E, ux, tot, uz, &slot, &flags);
-            W = r2.x;
-            om = r2.y;
+            const float4 r4 = table_event_call<S>(P, e.E, ux, tot, uz, slot, flags);
+            W = r4.x;
+            om = r4.y;
+            slot = __float_as_int(r4.z);
+            flags = __float_as_int(r4.w);
             done = true;
           }
         }
-        n_pend += min(__popc(pm), room);
+        wst += (uint32_t)min(__popc(pm), room) << 8;
         __syncwarp();
       }
     }
@@ -530,15 +536,18 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
     }
     if (done) {
       rotate_dir(e.dx, e.dy, e.dz, e.yx, e.yy, e.yz, c2, om, uphi);
-      if (want_chan) atomicAdd(&s_cnt[kCntChan + slot_channel(P.m, slot)], 1ull);
+      if (want_chan) atomicAdd(&s_cnt[kCntChan + slot_channel(P.m, slot)], 1u);
       if (flags & (MCD_EVF_NANCLAMP | MCD_EVF_EXACT)) {
-        if (flags & MCD_EVF_NANCLAMP) atomicAdd(&s_cnt[kCntNan], 1ull);
-        if (flags & MCD_EVF_EXACT) atomicAdd(&s_cnt[kCntExact], 1ull);
+        if (flags & MCD_EVF_NANCLAMP) atomicAdd(&s_cnt[kCntNan], 1u);
+        if (flags & MCD_EVF_EXACT) atomicAdd(&s_cnt[kCntExact], 1u);
       }
       ++ev;
     }
   }
 
+#undef n_ready
+#undef n_pend
+#undef exhausted
   __syncthreads();
   flush_block_stats(O, s_hist, s_cnt, nullptr, false, want_chan);
 }
