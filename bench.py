@@ -215,7 +215,7 @@ def main():
     # step k+1 fill the SMs that the tail of step k leaves idle (1e6 electrons are only 5.9 per resident lane) and
     # the tail hand-over passes of one step (sparse: the last electrons of a step are serial chains of up to
     # ~870 events) run behind the main pass of another
-    NPIPE = 4
+    NPIPE = 6
     engs = [eng] + [eng.clone() for _ in range(NPIPE - 1)]
     tstreams = [torch.cuda.Stream() for _ in range(NPIPE)]
     for e in engs:

@@ -178,11 +178,13 @@ traj_kernel(const __grid_constant__ DevParams P, const DevOut O, const unsigned 
     row.slot = 0;
     row.E = e.E;
     if (has_row) {
+      HotRec hr;
+      if (MODE == MCD_MODE_DS) hr = ds_hot_fetch(P, e.E);          // loads first, Philox hides their latency
       const float4 u = event_uniforms(P, first_id + rel_id, ev);
       if (MODE == MCD_MODE_DS) {
         EventMid mid;
         float tot;
-        ds_phase_a<S>(P, e, u, row, mid, tot);
+        ds_phase_a<S>(P, e, u, row, mid, tot, hr);
         ds_phase_b<S>(P, e, u, row, mid, tot);
       } else {
         cont_event(P, e, u, row);
@@ -478,9 +480,10 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
       float uz = 0.f, ux = 0.f, tot = 0.f;
       EventRow row;
       if (has_row) {
+        const HotRec hr = ds_hot_fetch(P, e.E);                     // loads first, Philox hides their latency
         const float4 u = event_uniforms(P, first_id + rel_id, ev);
         EventMid mid;
-        ds_phase_a<S>(P, e, u, row, mid, tot);
+        ds_phase_a<S>(P, e, u, row, mid, tot, hr);
         outcome = row.outcome;
         slot = row.slot;
         flags = row.flags;
@@ -782,7 +785,7 @@ cudaError_t mcd_launch_traj(const DevParams& P, const DevOut& O_in, unsigned lon
   // tail hand-over (park-pool kernel only): pass 0 runs the fresh ids and dumps what its warps still hold when they
   // are down to dump_T electrons; passes 1..n-1 run the leftover queue of the pass before; the last pass does not
   // dump.  MCD_DUMP_T=0 or MCD_PASSES=1: one launch.
-  static const int env_T = getenv("MCD_DUMP_T") ? atoi(getenv("MCD_DUMP_T")) : 24;
+  static const int env_T = getenv("MCD_DUMP_T") ? atoi(getenv("MCD_DUMP_T")) : 31;
   static const int env_passes = getenv("MCD_PASSES") ? atoi(getenv("MCD_PASSES")) : 3;
   int passes = 1;
   int dump_T = 0;

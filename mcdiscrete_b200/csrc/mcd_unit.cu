@@ -167,7 +167,7 @@ __device__ void step_one(const DevParams& P, bool on, ElState& e, float4 u, Even
   if (P.mode == MCD_MODE_DS) {
     EventMid mid;
     float tot;
-    ds_phase_a<S>(P, e, u, row, mid, tot);
+    ds_phase_a<S>(P, e, u, row, mid, tot, ds_hot_fetch(P, e.E));
     ds_phase_b<S>(P, e, u, row, mid, tot);
   } else {
     cont_event(P, e, u, row);

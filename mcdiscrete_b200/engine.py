@@ -380,7 +380,7 @@ class Engine:
 
     def run_batches(self, total, batch, first_id=0, max_scat_rows=None, on_launched=None, ordered=False, depth=None):
         """Simulate `total` electrons in batches of `batch`, PIPELINED over `depth` contexts / CUDA streams
-        (default 4 for statistics-only runs, 2 when scats rows are recorded): while the host drains batch k
+        (default 6 for statistics-only runs, 2 when scats rows are recorded): while the host drains batch k
         (D2H into pinned buffers) the next batches already run, their blocks fill the SMs that the tail of batch k
         leaves idle, and the tail hand-over passes of one batch hide behind the main pass of another.  Yields
         one RunResult per batch, in order.  Rows of a yielded result live in reused pinned buffers: consume them
@@ -392,7 +392,7 @@ class Engine:
         if self.params.mode == _lib.MODE_DS and self.tables is None:
             from .probTables import genTables
             genTables(self.inputPar, engine=self)
-        depth = int(depth or (2 if self.row_words else 4))
+        depth = int(depth or (2 if self.row_words else 6))
         # the extra contexts, their device buffers, the pinned staging buffers and the streams are kept for
         # later calls (creating them costs tens of milliseconds of cudaMalloc / page-locking)
         pipe = getattr(self, '_pipe', None)

@@ -518,7 +518,7 @@ def test_statistics_only_kernel_equals_row_recording_kernel(kw, n):
 
 
 def test_pipelined_statistics_only_batches():
-    """run_batches at its default depth (4 contexts / streams) for a statistics-only run: every batch complete, rows
+    """run_batches at its default depth (6 contexts / streams) for a statistics-only run: every batch complete, rows
     equal to one big run."""
     from mcdiscrete_b200.probTables import genTables
     ip = base_input(scatter_output=[], Emin=10000.)
