@@ -338,7 +338,7 @@ def main():
             last = r                                  # rows are in pinned host memory here
             _ = int(r.els['code'][0]) + r.counters['events']
         return last
-    e2e_pass(2)
+    e2e_pass(NPIPE + 2)                               # warm every context of the pipeline (device buffers, pinned staging)
     barrier()
     t0 = time.time()
     r = e2e_pass(args.steps)
