@@ -414,21 +414,24 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
     // 7..870 events long, so without this every warp (and its block's slot on the SM) lingers for ~800 iterations
     // at an average of 12 live lanes.  Parked electrons are searched first (forced batch), so the queue only holds
     // plain states. ---------------------------------------------------------------------------------------------
-    const bool tail = exhausted && (a + n_pend <= O.dump_T);
-    if (tail && n_pend == 0) {
-      const int leader = __ffs(am) - 1;
-      unsigned long long base = 0ull;
-      if ((int)lane == leader) base = atomicAdd(O.rq_out_count, (unsigned long long)a);
-      base = __shfl_sync(MCD_FULL_MASK, base, leader);
-      if (alive) {
-        uint32_t* q = O.rq_out + (base + (unsigned long long)__popc(am & lt));
+    bool tail = false;
+    if (exhausted) {
+      tail = (a + n_pend <= O.dump_T);
+      if (tail && n_pend == 0) {
+        const int leader = __ffs(am) - 1;
+        unsigned long long base = 0ull;
+        if ((int)lane == leader) base = atomicAdd(O.rq_out_count, (unsigned long long)a);
+        base = __shfl_sync(MCD_FULL_MASK, base, leader);
+        if (alive) {
+          uint32_t* q = O.rq_out + (base + (unsigned long long)__popc(am & lt));
 #define MCD_STQ(w, f) q[(size_t)(w) * O.rq_cap] = __float_as_uint(f);
-        MCD_POOL_EACH_STATE(MCD_STQ)
+          MCD_POOL_EACH_STATE(MCD_STQ)
 #undef MCD_STQ
-        q[(size_t)10 * O.rq_cap] = rel_id;
-        q[(size_t)11 * O.rq_cap] = ev;
+          q[(size_t)10 * O.rq_cap] = rel_id;
+          q[(size_t)11 * O.rq_cap] = ev;
+        }
+        break;
       }
-      break;
     }
 
     bool done = false;                             // this lane completes an event in this iteration
@@ -499,9 +502,11 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
       if (pm) {
         const int room = kPoolSlots - n_ready - n_pend;
         const int r = __popc(pm & lt);
+        const int top = kPoolSlots - n_pend - 1;                 // first free slot of the parked stack
+        wst += (uint32_t)min(__popc(pm), room) << 8;             // (before the branches: nothing lives across the call)
         if (park) {
           if (r < room) {
-            uint32_t* w = pool + (kPoolSlots - n_pend - 1 - r) * kSlotWords;
+            uint32_t* w = pool + (top - r) * kSlotWords;
             pool_put(w, e, rel_id, ev | ((uint32_t)slot << 24) | ((uint32_t)(outcome + 1) << 28) | ((uint32_t)(flags & 1) << 31));
             *reinterpret_cast<uint4*>(w + 12) = make_uint4(__float_as_uint(uz), __float_as_uint(uphi), __float_as_uint(ux), __float_as_uint(tot));
             alive = false;
@@ -516,14 +521,12 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
             done = true;
           }
         }
-        wst += (uint32_t)min(__popc(pm), room) << 8;
         __syncwarp();
       }
     }
 
     // ---- energy update (electron.py:44-59), retire (saveOutcomes before the rotation), update_direction ---------
     const float preE = e.E;
-    const float c2 = 1.0f - om;
     if (done) {
       const float En = preE - W;
       if (En <= P.Emin) {
@@ -538,7 +541,7 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
       alive = false;
     }
     if (done) {
-      rotate_dir(e.dx, e.dy, e.dz, e.yx, e.yy, e.yz, c2, om, uphi);
+      rotate_dir(e.dx, e.dy, e.dz, e.yx, e.yy, e.yz, 1.0f - om, om, uphi);
       if (want_chan) atomicAdd(&s_cnt[kCntChan + slot_channel(P.m, slot)], 1u);
       if (flags & (MCD_EVF_NANCLAMP | MCD_EVF_EXACT)) {
         if (flags & MCD_EVF_NANCLAMP) atomicAdd(&s_cnt[kCntNan], 1u);
