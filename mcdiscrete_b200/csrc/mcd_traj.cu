@@ -406,9 +406,9 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
         if (base + (unsigned long long)nreq >= count) wst |= 0x10000u;
       }
     }
-    const unsigned am = __ballot_sync(MCD_FULL_MASK, alive);
-    const int a = __popc(am);
-    if (a == 0 && n_pend == 0) break;
+    // until the ids run out every lane holds an electron here (the refill above filled all of them)
+    unsigned am = MCD_FULL_MASK;
+    int a = 32;
     // ---- tail: once the ids have run out a warp that is down to dump_T electrons hands them to the next pass
     // (leftover queue in global memory) and leaves; that pass runs them in full warps again.  A trajectory is
     // 7..870 events long, so without this every warp (and its block's slot on the SM) lingers for ~800 iterations
@@ -416,6 +416,9 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
     // plain states. ---------------------------------------------------------------------------------------------
     bool tail = false;
     if (exhausted) {
+      am = __ballot_sync(MCD_FULL_MASK, alive);
+      a = __popc(am);
+      if (a == 0 && n_pend == 0) break;
       tail = (a + n_pend <= O.dump_T);
       if (tail && n_pend == 0) {
         const int leader = __ffs(am) - 1;
