@@ -50,7 +50,13 @@ typedef enum {
 /* mode / model enums (input.file keys `mode`, `Bethe_model`, `elastic`; MC/tools/fileTools.py:27) */
 enum { MCD_MODE_DS = 0, MCD_MODE_CONT = 1 };
 enum { MCD_BETHE_CLASSICAL = 0, MCD_BETHE_JL = 1, MCD_BETHE_EXPLICIT = 2 };
-enum { MCD_ELASTIC_RUTH_VANILLA = 0 };
+/* elastic cross-section EVALUATED for the 'Ruth' channel (crossSections.py:37-58, 63-84, 89-112, 115-143).  The
+ * reference's label -> function rules differ between DS (scattering.py:483-491) and continuous mode
+ * (scattering.py:781-789, where the _wDefl branches are unreachable); the host mirror applies them
+ * (mcdiscrete_b200/engine.py::elastic_kind).  The polar angle is Rutherford_halfPol with the vanilla screening
+ * parameter for every model (scattering.py:575-577, :829). */
+enum { MCD_ELASTIC_RUTH_VANILLA = 0, MCD_ELASTIC_RUTH_VANILLA_WDEFL = 1, MCD_ELASTIC_RUTH_NIGRAM = 2,
+       MCD_ELASTIC_RUTH_NIGRAM_WDEFL = 3 };
 /* tables['Gryz'][0] is read for EVERY shell in the reference (scattering.py:625) */
 enum { MCD_GRYZ_OUTERMOST = 0, MCD_GRYZ_PER_SHELL = 1 };
 /* table slots: 0 = Moller, 1 + k = Gryzinski table k in the reference's tables['Gryz'] order

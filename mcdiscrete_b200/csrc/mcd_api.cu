@@ -106,9 +106,17 @@ double gryz_sigma_host(double E, double Es, double ns) {          // crossSectio
 }
 
 // sigma formulas in float64 (crossSections.py:37-58, 183-208, 247-284) for the host-side order proof
-double ruth_sigma_host(double E, double Z) {
+// elastic: ruther_sigma :37-58, ruther_sigma_wDefl :63-84 (Z^2 -> Z(Z+1)), ruther_N_sigma :89-112 and
+// ruther_N_sigma_wDefl :115-143 (Nigam screening beta* = 0.48 * 5.43 Z^(2/3) / E)
+double ruth_sigma_host(double E, double Z, int elastic) {
+  const double zz = (elastic == MCD_ELASTIC_RUTH_VANILLA_WDEFL || elastic == MCD_ELASTIC_RUTH_NIGRAM_WDEFL)
+                        ? Z * (Z + 1.) : Z * Z;
+  if (elastic == MCD_ELASTIC_RUTH_NIGRAM || elastic == MCD_ELASTIC_RUTH_NIGRAM_WDEFL) {
+    const double b = 0.48 * (5.43 * pow(Z, 2. / 3.) / E);
+    return kPiEFour * zz / (4. * b * (1. + b) * E * E);
+  }
   const double a = 3.4 * pow(Z, 0.666667) / E, Ek = E * 1e-3, r = (Ek + 511.) / (Ek + 1024.);
-  return 5.21e-21 * (Z * Z / (Ek * Ek)) * r * r * (4. * M_PI) / (a * (1. + a));
+  return 5.21e-21 * (zz / (Ek * Ek)) * r * r * (4. * M_PI) / (a * (1. + a));
 }
 double moller_sigma_host(double E, double Wc, double nfree) {
   if (E <= Wc) return 0.;
@@ -128,7 +136,7 @@ int order_is_static(const mcd_params& p, const mcd_material& mt, const int* orde
   for (int i = 0; i < n; ++i) {
     const double E = p.Emin * pow(p.E0 / p.Emin, (double)i / (n - 1));
     double s[MCD_MAX_CHANNELS];
-    s[0] = ruth_sigma_host(E, mt.Z);
+    s[0] = ruth_sigma_host(E, mt.Z, p.elastic);
     s[1] = quinn_sigma_host(E, mt.plasmon_e, mt.fermi_e, mt.atnd);
     s[2] = moller_sigma_host(E, p.Wc, mt.n_val);
     for (int k = 0; k < mt.n_shells; ++k) s[3 + k] = gryz_sigma_host(E, mt.shell_E[order[k]], mt.shell_n[order[k]]);
@@ -141,7 +149,7 @@ int order_is_static(const mcd_params& p, const mcd_material& mt, const int* orde
 // cumulative inverse mean free paths (1/Angstrom) in slot order at energy E, float64
 void cum_host(const mcd_params& p, const mcd_material& mt, const int* order, double E, double* cum) {
   const double scale = mt.atnd * 1e-14;
-  double c = ruth_sigma_host(E, mt.Z) * scale;
+  double c = ruth_sigma_host(E, mt.Z, p.elastic) * scale;
   cum[0] = c;
   c += quinn_sigma_host(E, mt.plasmon_e, mt.fermi_e, mt.atnd) * scale;
   cum[1] = c;
@@ -305,7 +313,20 @@ void build_dev_params(mcd_ctx* c) {
   m.sig_scale_inv = (float)(1.0 / scale);
   const double aZ = 3.4 * pow(Z, 0.666667);                        // crossSections.py:27
   m.aZ = (float)aZ;
-  m.cR = (float)(5.21e-21 * Z * Z * 1e6 * 4.0 * M_PI * scale / aZ);
+  const double zz = (p.elastic == MCD_ELASTIC_RUTH_VANILLA_WDEFL || p.elastic == MCD_ELASTIC_RUTH_NIGRAM_WDEFL)
+                        ? Z * (Z + 1.0) : Z * Z;
+  if (p.elastic == MCD_ELASTIC_RUTH_NIGRAM || p.elastic == MCD_ELASTIC_RUTH_NIGRAM_WDEFL) {
+    // pi e^4 zz / (4 b*/E (1 + b*/E) E^2) = pi e^4 zz / (4 b* (E + b*)),  b* = 0.48 * 5.43 Z^(2/3)
+    const double bN = 0.48 * 5.43 * pow(Z, 2.0 / 3.0);
+    m.aS = (float)bN;
+    m.rN = m.rD = 0.0f;                                            // no relativistic factor: (E/E)^2
+    m.cR = (float)(kPiEFour * zz * scale / (4.0 * bN));
+  } else {
+    m.aS = (float)aZ;
+    m.rN = 511000.0f;
+    m.rD = 1024000.0f;
+    m.cR = (float)(5.21e-21 * zz * 1e6 * 4.0 * M_PI * scale / aZ);
+  }
   m.cM = (float)(mt.n_val * kPiEFour * scale);
   m.Wc = (float)p.Wc;
   m.invWc = (float)(1.0 / p.Wc);
@@ -513,8 +534,8 @@ int mcd_create(const mcd_params* p, const mcd_material* m, int device, mcd_ctx**
     return fail(nullptr, MCD_ERR_INVALID, "n_shells=%d outside 1..%d", m->n_shells, MCD_MAX_SHELLS);
   if (p->mode != MCD_MODE_DS && p->mode != MCD_MODE_CONT) return fail(nullptr, MCD_ERR_INVALID, "bad mode %d", p->mode);
   if (p->bethe < 0 || p->bethe > 2) return fail(nullptr, MCD_ERR_INVALID, "bad Bethe model %d", p->bethe);
-  if (p->elastic != MCD_ELASTIC_RUTH_VANILLA)
-    return fail(nullptr, MCD_ERR_INVALID, "only elastic = Ruth_vanilla is implemented");
+  if (p->elastic < MCD_ELASTIC_RUTH_VANILLA || p->elastic > MCD_ELASTIC_RUTH_NIGRAM_WDEFL)
+    return fail(nullptr, MCD_ERR_INVALID, "bad elastic model %d (Mott / Browning are not on the path)", p->elastic);
   if (!(p->E0 > p->Emin) || !(p->Emin > 0)) return fail(nullptr, MCD_ERR_INVALID, "need E0 > Emin > 0");
   if (p->mode == MCD_MODE_DS && !(p->Emin > m->plasmon_e))
     return fail(nullptr, MCD_ERR_INVALID, "DS needs Emin > plasmon energy (quinn_sigma, crossSections.py:272-281)");

@@ -113,6 +113,25 @@ class RunResult:
         return ScatRows(w[order], self.scats.word_of, self.scats.first_id, off)
 
 
+ELASTIC_MODELS = ('Ruth_vanilla', 'Ruth_vanilla_wDefl', 'Ruth_nigram', 'Ruth_nigram_wDefl')
+
+
+def elastic_kind(elastic, ds):
+    """input.file `elastic` label -> the cross-section the reference evaluates for it (MCD_ELASTIC_* of mcd.h).
+    DS (scattering.py:483-491): Ruth_vanilla -> ruther_sigma, *vanilla_wDefl -> ruther_sigma_wDefl (raises NameError
+    in the reference because scattering.py:14 does not import it; the intended function is used here), Ruth_nigram ->
+    ruther_N_sigma, *nigram_wDefl -> ruther_N_sigma_wDefl.  Continuous mode (scattering.py:781-789) tests the
+    substrings 'vanilla', 'vanilla_wDefl', 'nigram', 'nigram_wDefl' in that order, so its _wDefl branches are
+    unreachable and those labels run the plain forms (tests/golden/elastic_formulas.json records both facts).
+    Mott / Browning need unshipped data or crash."""
+    if elastic not in ELASTIC_MODELS:
+        raise NotImplementedError("elastic = %r: only %s are on the path (Mott / Browning need unshipped data or "
+                                  "crash in the reference, SURVEY Q10)" % (elastic, ', '.join(ELASTIC_MODELS)))
+    if not ds:
+        elastic = 'Ruth_vanilla' if 'vanilla' in elastic else 'Ruth_nigram'
+    return ELASTIC_MODELS.index(elastic)
+
+
 class Engine:
     def __init__(self, inputPar, material=None, device=None, seed=None, gryz_table='outermost',
                  histograms=True, channel_counts=False):
@@ -147,10 +166,7 @@ class Engine:
         if bm not in _lib.BETHE:
             raise ValueError('! I did not understand your choice of Bethe model: %r' % bm)
         p.bethe = _lib.BETHE[bm]
-        if ip.get('elastic', 'Ruth_vanilla') != 'Ruth_vanilla':
-            raise NotImplementedError("only elastic = 'Ruth_vanilla' is implemented (others crash or need "
-                                      "unshipped data in the reference, SURVEY Q10)")
-        p.elastic = 0
+        p.elastic = elastic_kind(ip.get('elastic', 'Ruth_vanilla'), p.mode == _lib.MODE_DS)
         p.gryz_table_mode = 1 if gryz_table == 'per_shell' else 0
         self.el_cols = list(ip.get('electron_output', ['outcome', 'final_E', 'final_dir', 'last_pos']))
         self.scat_cols = list(ip.get('scatter_output', []))

@@ -90,6 +90,42 @@ def ruther_sigma(E, Z):
     return 5.21e-21 * (Z * Z / (Ek * Ek)) * ((Ek + 511.) / (Ek + 1024.)) ** 2 * (4. * math.pi) / (a * (1. + a))
 
 
+def ruther_sigma_wDefl(E, Z):
+    """crossSections.py:63-84: Z**2 -> Z*(Z+1)."""
+    a = alpha(E, Z)
+    Ek = E * 1e-3
+    return 5.21e-21 * (Z * (Z + 1) / (Ek * Ek)) * ((Ek + 511.) / (Ek + 1024.)) ** 2 * (4. * math.pi) / (a * (1. + a))
+
+
+def ruther_N_sigma(E, Z):
+    """crossSections.py:89-112 (Nigam screening, beta* = 0.48 beta_N)."""
+    b = 0.48 * (5.43 * Z ** (2 / 3) / E)
+    return PI_EFOUR * Z ** 2 / (4 * b * (1 + b) * E ** 2)
+
+
+def ruther_N_sigma_wDefl(E, Z):
+    """crossSections.py:115-143."""
+    b = 0.48 * (5.43 * Z ** (2 / 3) / E)
+    return PI_EFOUR * (Z + 1) * Z / (4 * b * (1 + b) * E ** 2)
+
+
+ELASTIC_MODELS = ('Ruth_vanilla', 'Ruth_vanilla_wDefl', 'Ruth_nigram', 'Ruth_nigram_wDefl')
+
+
+def elastic_sigma(E, Z, elastic='Ruth_vanilla', mode='DS'):
+    """The elastic cross-section the reference evaluates for an `elastic` label.
+    DS (scattering.py:483-491): exact label match / 'vanilla_wDefl' / 'nigram_wDefl'.  'Ruth_vanilla_wDefl'
+    raises NameError there (ruther_sigma_wDefl is not imported, scattering.py:14); the intended function is used.
+    Continuous (scattering.py:781-789): substring tests in the order 'vanilla', 'vanilla_wDefl', 'nigram',
+    'nigram_wDefl', so the two _wDefl branches are unreachable and the labels fall back to the plain forms."""
+    if elastic not in ELASTIC_MODELS:
+        raise ValueError('elastic model %r is not on the path' % (elastic,))
+    if mode != 'DS':
+        return ruther_sigma(E, Z) if 'vanilla' in elastic else ruther_N_sigma(E, Z)
+    return {'Ruth_vanilla': ruther_sigma, 'Ruth_vanilla_wDefl': ruther_sigma_wDefl,
+            'Ruth_nigram': ruther_N_sigma, 'Ruth_nigram_wDefl': ruther_N_sigma_wDefl}[elastic](E, Z)
+
+
 def moller_sigma(E, Wc, nfree):
     """crossSections.py:183-208."""
     if E <= Wc:
@@ -120,9 +156,9 @@ def mfp_from_sigma(sigma, n):
     return 1. / (n * sigma) * 1e14
 
 
-def sigmas_ds(E, mat, Wc):
+def sigmas_ds(E, mat, Wc, elastic='Ruth_vanilla'):
     """scattering.py:485-508: list in insertion order Ruth, Moller, Gryz<shell>..., Quinn."""
-    s = [ruther_sigma(E, mat.Z), moller_sigma(E, Wc, mat.n_val)]
+    s = [elastic_sigma(E, mat.Z, elastic, 'DS'), moller_sigma(E, Wc, mat.n_val)]
     s += [gryz_sigma(E, mat.Es[i], mat.ns[i]) for i in range(len(mat.Es))]
     s.append(quinn_sigma(E, mat.plasmon_e, mat.fermi_e, mat.atnd))
     return s
@@ -514,12 +550,12 @@ def initial_dir(s_tilt_deg):
     return np.array([-np.sin(t), 0., np.cos(t)])
 
 
-def ds_event(el, mat, Wc, thickness, tables, us, gryz_per_shell=False):
+def ds_event(el, mat, Wc, thickness, tables, us, gryz_per_shell=False, elastic='Ruth_vanilla'):
     """One iteration of the trajectory_DS loop body after the maxScatt check
     (singleScatter.py:25-41 + scattering.py:530-679).  ``us`` = (u_type, u_path, u_channel, u_phi);
     u_channel is unused for Quinn.  Returns the scats row."""
     E = el.energy
-    sig = sigmas_ds(E, mat, Wc)
+    sig = sigmas_ds(E, mat, Wc, elastic)
     mfp = mfp_from_sigma(sum(sig), mat.atnd)                               # scattering.py:519
     row = {'position': el.xyz.copy(), 'E': E}
     ch = pick_from_sigmas(sig, us[0])                                      # :530-549
@@ -555,7 +591,8 @@ def ds_event(el, mat, Wc, thickness, tables, us, gryz_per_shell=False):
     return row
 
 
-def trajectory_ds(el, mat, Wc, maxScatt, thickness, tables, uniforms, gryz_per_shell=False):
+def trajectory_ds(el, mat, Wc, maxScatt, thickness, tables, uniforms, gryz_per_shell=False,
+                  elastic='Ruth_vanilla'):
     """singleScatter.py:10-41.  ``uniforms(ev_idx)`` -> 4 uniforms for that event."""
     n = 0
     while el.outcome not in OUTCOMES:
@@ -564,14 +601,14 @@ def trajectory_ds(el, mat, Wc, maxScatt, thickness, tables, uniforms, gryz_per_s
             el.outcome = 'long'
             el.save_outcomes()
             return
-        el.scats.append(ds_event(el, mat, Wc, thickness, tables, uniforms(n - 1), gryz_per_shell))
+        el.scats.append(ds_event(el, mat, Wc, thickness, tables, uniforms(n - 1), gryz_per_shell, elastic))
 
 
-def cont_event(el, mat, thickness, model, us):
+def cont_event(el, mat, thickness, model, us, elastic='Ruth_vanilla'):
     """trajectory_cont_cl loop body (singleScatter.py:220-239 + scattering.py:802-840).
     ``us`` = (u_path, u_polar, u_phi)."""
     E = el.energy
-    mfp = mfp_from_sigma(ruther_sigma(E, mat.Z), mat.atnd)                 # scattering.py:783-792
+    mfp = mfp_from_sigma(elastic_sigma(E, mat.Z, elastic, 'cont'), mat.atnd)   # scattering.py:781-792
     pathl = -mfp * math.log(us[0])                                         # :807
     row = {'pathl': pathl}
     el.update_xyz(pathl, thickness)
@@ -581,13 +618,13 @@ def cont_event(el, mat, thickness, model, us):
     row['energy'] = el.energy
     c2 = rutherford_halfpol(E, mat.Z, us[1])                               # :829
     halfPhi = math.pi * us[2]                                              # :831
-    row.update(type='Ruth_vanilla', channel=0, pol_angle=c2, az_angle=halfPhi)
+    row.update(type=elastic, channel=0, pol_angle=c2, az_angle=halfPhi)    # :834
     el.dir, el.y_local = update_direction(el.dir, el.y_local, c2, halfPhi)
     row['direction'] = el.dir.copy()
     return row
 
 
-def trajectory_cont(el, mat, maxScatt, thickness, model, uniforms):
+def trajectory_cont(el, mat, maxScatt, thickness, model, uniforms, elastic='Ruth_vanilla'):
     """singleScatter.py:205-239 (exits on abs/bks/trsm; 'long' returns)."""
     n = 0
     while el.outcome not in ('abs', 'bks', 'trsm'):
@@ -596,7 +633,7 @@ def trajectory_cont(el, mat, maxScatt, thickness, model, uniforms):
             el.outcome = 'long'
             el.save_outcomes()
             return
-        el.scats.append(cont_event(el, mat, thickness, model, uniforms(n - 1)))
+        el.scats.append(cont_event(el, mat, thickness, model, uniforms(n - 1), elastic))
 
 
 def run_electrons(inputPar, first_id, count, seed, tables=None, mat=None, gryz_per_shell=False):
@@ -604,15 +641,17 @@ def run_electrons(inputPar, first_id, count, seed, tables=None, mat=None, gryz_p
     ``random.seed(pid*time)`` (:94) replaced by Philox streams keyed on the electron id."""
     mat = mat or Material(inputPar['material'])
     d0 = initial_dir(inputPar['s_tilt'])
+    elastic = inputPar.get('elastic', 'Ruth_vanilla')
     out = []
     for eid in range(first_id, first_id + count):
         el = Electron(inputPar['E0'], inputPar['Emin'], (0., 0., 0.), d0)
         uni = lambda ev, eid=eid: event_uniforms(seed, eid, ev)
         if inputPar['mode'] == 'DS':
             trajectory_ds(el, mat, inputPar['Wc'], inputPar['maxScatt'], inputPar['thickness'], tables, uni,
-                          gryz_per_shell)
+                          gryz_per_shell, elastic)
         else:
             u3 = lambda ev, uni=uni: uni(ev)[:3]
-            trajectory_cont(el, mat, inputPar['maxScatt'], inputPar['thickness'], inputPar['Bethe_model'], u3)
+            trajectory_cont(el, mat, inputPar['maxScatt'], inputPar['thickness'], inputPar['Bethe_model'], u3,
+                            elastic)
         out.append(el)
     return out

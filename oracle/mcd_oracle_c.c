@@ -35,6 +35,9 @@ typedef struct {
   int mode;  /* 0 DS, 1 cont */
   int bethe; /* 0 classical, 1 JL, 2 explicit */
   unsigned long long seed;
+  int elastic; /* sigma evaluated for the elastic channel: 0 ruther_sigma, 1 ruther_sigma_wDefl, 2 ruther_N_sigma,
+                  3 ruther_N_sigma_wDefl (the label -> function mapping of scattering.py:483-491 / :781-789 is done
+                  by the caller, oracle/mcd_oracle.py::elastic_sigma) */
 } orc_par;
 
 static const double PI_EFOUR = 6.51408491409531e-14; /* parameters.py:7 */
@@ -56,6 +59,12 @@ static double alpha_(double E, double Z) { return 3.4 * pow(Z, 0.666667) / E; } 
 static double ruther_sigma(double E, double Z) {                                              /* :37-58 */
   double a = alpha_(E, Z), Ek = E * 1e-3, r = (Ek + 511.) / (Ek + 1024.);
   return 5.21e-21 * (Z * Z / (Ek * Ek)) * (r * r) * (4. * M_PI) / (a * (1. + a));
+}
+static double elastic_sigma(int kind, double E, double Z) {
+  if (kind == 0) return ruther_sigma(E, Z);
+  if (kind == 1) return ruther_sigma(E, Z) / (Z * Z) * (Z * (Z + 1.));                       /* :63-84 */
+  double b = 0.48 * (5.43 * pow(Z, 2. / 3.) / E);                                             /* :89-143 */
+  return PI_EFOUR * (kind == 2 ? Z * Z : (Z + 1.) * Z) / (4 * b * (1 + b) * (E * E));
 }
 static double moller_sigma(double E, double Wc, double nfree) {                               /* :183-208 */
   if (E <= Wc) return 0.;
@@ -161,7 +170,7 @@ static void one_electron(const orc_par* p, const orc_mat* m, const orc_tab* tm, 
     double pos0[3] = {xyz[0], xyz[1], xyz[2]};
     if (p->mode == 0) {
       double sig[ORC_MAX_CH], tot = 0.;
-      sig[0] = ruther_sigma(E, m->Z);
+      sig[0] = elastic_sigma(p->elastic, E, m->Z);
       sig[1] = moller_sigma(E, p->Wc, m->n_val);
       for (int i = 0; i < m->nshell; ++i) sig[2 + i] = gryz_sigma(E, m->Es[i], m->ns[i]);
       sig[nch - 1] = quinn_sigma(E, m->Epl, m->Ef, m->atnd, m->bohr_r);
@@ -170,7 +179,7 @@ static void one_electron(const orc_par* p, const orc_mat* m, const orc_tab* tm, 
       ch = pick_from_sigmas(sig, nch, u0);
       pathl = -mfp * log(u1);
     } else {
-      double mfp = 1. / (m->atnd * ruther_sigma(E, m->Z)) * 1e14;
+      double mfp = 1. / (m->atnd * elastic_sigma(p->elastic, E, m->Z)) * 1e14;
       pathl = -mfp * log(u0);
     }
     /* update_xyz (electron.py:64-84) */

@@ -25,7 +25,7 @@ class CTab(C.Structure):
 class CPar(C.Structure):
     _fields_ = [('E0', C.c_double), ('Emin', C.c_double), ('tilt_deg', C.c_double), ('thickness', C.c_double),
                 ('Wc', C.c_double), ('maxScatt', C.c_long), ('mode', C.c_int), ('bethe', C.c_int),
-                ('seed', C.c_ulonglong)]
+                ('seed', C.c_ulonglong), ('elastic', C.c_int)]
 
 
 _lib = None
@@ -58,9 +58,13 @@ def run(inputPar, first_id, count, seed, tables=None, mat=None, nthreads=1, even
     for i, (e, n) in enumerate(zip(mat.Es, mat.ns)):
         m.Es[i], m.ns[i] = e, n
     ds = inputPar['mode'] == 'DS'
+    el = inputPar.get('elastic', 'Ruth_vanilla')
+    if not ds:                                        # scattering.py:781-789: the _wDefl branches are unreachable
+        el = 'Ruth_vanilla' if 'vanilla' in el else 'Ruth_nigram'
     p = CPar(inputPar['E0'], inputPar['Emin'], inputPar['s_tilt'], inputPar['thickness'], inputPar.get('Wc', 10.),
              int(inputPar['maxScatt']), 0 if ds else 1,
-             {'classical': 0, 'JL': 1, 'explicit': 2}[inputPar.get('Bethe_model', 'classical')], seed)
+             {'classical': 0, 'JL': 1, 'explicit': 2}[inputPar.get('Bethe_model', 'classical')], seed,
+             o.ELASTIC_MODELS.index(el))
     tm = _tab(tables['Moller']) if ds else None
     tg = _tab(tables['Gryz'][0]) if ds else None
     els = np.empty((count, 9), np.float64)

@@ -582,3 +582,86 @@ def test_cumulative_cross_sections_of_the_hot_path(name, E0, Emin):
     assert rel[:, :2].max() < 2e-6
     assert (np.diff(cum, axis=1) >= 0).all()
     eng.close()
+
+
+# ---- alternative elastic models (crossSections.py:63-143, scattering.py:483-491, 781-789) ------------
+@pytest.mark.parametrize('elastic', o.ELASTIC_MODELS)
+def test_elastic_models_sigmas(elastic):
+    F = json.load(open(os.path.join(GOLD, 'elastic_formulas.json')))
+    key = elastic[5:]
+    for name in ('Al', 'Si', 'Cu', 'Au'):
+        m = o.Material(name)
+        rows = [r for r in F['rows'] if r['material'] == name]
+        rng = np.random.default_rng(3)
+        E = np.concatenate([[r['E'] for r in rows], rng.uniform(300., 30000., 2000)]).astype(np.float32)
+        for mode in ('DS', 'cont'):
+            eng = make_engine(material=name, Emin=250., mode=mode, elastic=elastic)
+            sig, mfp = eng.test_sigmas(E)
+            want = np.array([o.elastic_sigma(float(e), m.Z, elastic, mode) for e in E])
+            assert relerr(sig[:, 0], want).max() < REL
+            if mode == 'DS':                                     # the reference's own numbers
+                assert relerr(sig[:len(rows), 0], [r[key] for r in rows]).max() < REL
+                ref_mfp = [o.mfp_from_sigma(sum(o.sigmas_ds(float(e), m, 10., elastic)), m.atnd) for e in E]
+                assert relerr(mfp, ref_mfp).max() < REL
+            else:                                                # continuous: the _wDefl labels run the plain forms
+                assert relerr(sig[:len(rows), 0], [r[key.replace('_wDefl', '')] for r in rows]).max() < REL
+            eng.close()
+
+
+@pytest.mark.parametrize('elastic', ['Ruth_nigram', 'Ruth_nigram_wDefl'])
+def test_elastic_models_DS_trajectories_vs_reference_golden(elastic):
+    g = np.load(os.path.join(GOLD, 'traj_DS_Si_%s.npz' % elastic[5:]))
+    eng = make_engine(elastic=elastic)
+    upload_golden(eng, golden_tables('Si_15k_small'))
+    _golden_traj_check(eng, g, g['ids'])
+    eng.close()
+    # statistics-only kernel (hot / cold cross-section records built from the same model): identical els rows
+    a = make_engine(elastic=elastic)
+    b = make_engine(elastic=elastic, scatter_output=[])
+    for e in (a, b):
+        upload_golden(e, golden_tables('Si_15k_small'))
+    ra, rb = a.run(count=3000, first_id=0), b.run(count=3000, first_id=0)
+    assert np.array_equal(ra.els, rb.els) and ra.counters['events'] == rb.counters['events']
+    a.close()
+    b.close()
+
+
+@pytest.mark.parametrize('elastic', ['Ruth_nigram', 'Ruth_nigram_wDefl', 'Ruth_vanilla_wDefl'])
+def test_elastic_models_cont_trajectories_vs_reference_golden(elastic):
+    fname = 'traj_cont_Al_nigram.npz' if 'nigram' in elastic else 'traj_cont_Al_classical.npz'
+    g = np.load(os.path.join(GOLD, fname))
+    eng = make_engine(material='Al', Emin=500., mode='cont', Bethe_model='classical', maxScatt=100000, elastic=elastic,
+                      scatter_output=['type', 'pathl', 'E_loss', 'pol_angle', 'az_angle', 'energy', 'direction'])
+    _golden_traj_check(eng, g, g['ids'], atol_pos=2.0)
+    eng.close()
+
+
+@pytest.mark.parametrize('elastic', o.ELASTIC_MODELS[1:])
+def test_elastic_models_hot_path_cells_and_statistics(elastic):
+    """The per-cell cumulative cross-sections are built from the selected model, and a full DS run agrees with the
+    float64 C oracle run on other electrons (backscatter coefficient within 3 sigma)."""
+    import mcd_oracle_cbind as oc
+    ip = base_input(elastic=elastic, scatter_output=[])
+    eng = make_engine(elastic=elastic, scatter_output=[])
+    m = o.Material('Si')
+    E = np.random.default_rng(2).uniform(15000., 20000., 5000).astype(np.float32)
+    cum, slot_ch, uses_poly, err = eng.test_cum(E)
+    assert uses_poly and err < 1.5e-7
+    scale = m.atnd * 1e-14
+    ref = np.array([np.cumsum(np.array(o.sigmas_ds(float(e), m, 10., elastic))[slot_ch]) * scale for e in E])
+    assert (np.abs(cum - ref) / ref[:, -1:])[:, 2:].max() < 3e-7
+    g = golden_tables('Si_15k_small')
+    upload_golden(eng, g)
+    n_gpu, n_ref = 200000, 40000
+    res = eng.run(count=n_gpu, first_id=0)
+    ref_run = oc.run(ip, 10 ** 7, n_ref, 12345, oracle_tables(g), nthreads=os.cpu_count() or 1)
+    eta_g, eta_r = float((res.outcome == 1).mean()), float((ref_run['outcome'] == 1).mean())
+    sd = math.sqrt(eta_r * (1 - eta_r) * (1. / n_gpu + 1. / n_ref))
+    assert abs(eta_g - eta_r) < 3 * sd, (eta_g, eta_r, sd)
+    # the model matters: the vanilla backscatter coefficient is measurably different
+    van = make_engine(scatter_output=[])
+    upload_golden(van, g)
+    eta_v = float((van.run(count=n_gpu, first_id=0).outcome == 1).mean())
+    assert abs(eta_v - eta_g) > 3 * math.sqrt(eta_g * (1 - eta_g) * 2. / n_gpu), (eta_v, eta_g)
+    van.close()
+    eng.close()

@@ -56,6 +56,25 @@ def test_c_port_matches_python_port_cont(model):
     np.testing.assert_allclose(c['final_E'], [e.els[0][1] for e in py], rtol=1e-12)
 
 
+@pytest.mark.parametrize('elastic', o.ELASTIC_MODELS[1:])
+def test_c_port_matches_python_port_elastic_models(elastic):
+    """DS and continuous runs with the alternative elastic cross-sections."""
+    ip = dict(E0=20000., Emin=15000., material='Si', s_tilt=70., thickness=3e6, mode='DS', maxScatt=1000, Wc=10.,
+              elastic=elastic)
+    tabs = _golden_tabs('Si_15k_small')
+    py = o.run_electrons(ip, 7, 16, 4242, tabs)
+    c = oc.run(ip, 7, 16, 4242, tabs)
+    assert list(c['n_ev']) == [len(e.scats) for e in py]
+    assert list(c['outcome']) == [o.OUTCOMES.index(e.els[0][0]) for e in py]
+    np.testing.assert_allclose(c['final_E'], [e.els[0][1] for e in py], rtol=1e-12)
+    np.testing.assert_allclose(c['last_pos'], [e.els[0][3] for e in py], rtol=1e-10, atol=1e-8)
+    ipc = dict(ip, material='Al', Emin=500., mode='cont', Bethe_model='JL', maxScatt=100000)
+    py = o.run_electrons(ipc, 0, 8, 4242)
+    c = oc.run(ipc, 0, 8, 4242)
+    assert list(c['n_ev']) == [len(e.scats) for e in py]
+    np.testing.assert_allclose(c['final_E'], [e.els[0][1] for e in py], rtol=1e-12)
+
+
 def test_c_port_threads_and_q4():
     g = np.load(os.path.join(GOLD, 'traj_DS_Si_q4.npz'))
     T = {}

@@ -163,6 +163,49 @@ def test_trajectories_cont(model):
     _check_traj(g, els, ['pathl', 'E_loss', 'pol_angle', 'az_angle', 'energy', 'direction'], atol=1e-8)
 
 
+def test_elastic_models_formulas_and_reference_behaviour():
+    """the alternative elastic cross-sections (crossSections.py:63-143) and what the reference does
+    with each label (recorded by oracle/gen_golden_elastic.py)."""
+    F = json.load(open(os.path.join(GOLD, 'elastic_formulas.json')))
+    for r in F['rows']:
+        E, Z = r['E'], r['Z']
+        assert o.ruther_sigma(E, Z) == pytest.approx(r['vanilla'], rel=RTOL)
+        assert o.ruther_sigma_wDefl(E, Z) == pytest.approx(r['vanilla_wDefl'], rel=RTOL)
+        assert o.ruther_N_sigma(E, Z) == pytest.approx(r['nigram'], rel=RTOL)
+        assert o.ruther_N_sigma_wDefl(E, Z) == pytest.approx(r['nigram_wDefl'], rel=RTOL)
+        # continuous mode: the _wDefl branches are unreachable (scattering.py:781-789)
+        assert o.elastic_sigma(E, Z, 'Ruth_nigram_wDefl', 'cont') == o.ruther_N_sigma(E, Z)
+        assert o.elastic_sigma(E, Z, 'Ruth_vanilla_wDefl', 'cont') == o.ruther_sigma(E, Z)
+    b = F['reference_behaviour']
+    assert b['DS Ruth_vanilla_wDefl'].startswith('NameError')
+    assert b['cont Ruth_nigram_wDefl'] == 'identical to Ruth_nigram'
+    assert b['cont Ruth_vanilla_wDefl'] == 'identical to Ruth_vanilla'
+    with pytest.raises(ValueError):
+        o.elastic_sigma(2e4, 14, 'Mott')
+
+
+@pytest.mark.parametrize('elastic', ['Ruth_nigram', 'Ruth_nigram_wDefl'])
+def test_trajectories_DS_elastic_models(elastic):
+    g = load('traj_DS_Si_%s.npz' % elastic[5:])
+    ip = dict(E0=20000., Emin=15000., material='Si', s_tilt=70., thickness=3e6, mode='DS', maxScatt=1000, Wc=10.,
+              elastic=elastic)
+    mat = o.Material('Si')
+    tabs = _tables_from_golden('Si_15k_small', mat)
+    ids = g['ids']
+    els = o.run_electrons(ip, int(ids[0]), len(ids), 12345, tabs, mat)
+    _check_traj(g, els, ['type', 'position', 'pathl', 'E', 'E_loss', 'pol_angle', 'az_angle', 'energy', 'direction'])
+
+
+@pytest.mark.parametrize('elastic', ['Ruth_nigram', 'Ruth_nigram_wDefl'])
+def test_trajectories_cont_elastic_models(elastic):
+    g = load('traj_cont_Al_nigram.npz')                # the _wDefl label runs the same code in the reference
+    ip = dict(E0=20000., Emin=500., material='Al', s_tilt=70., thickness=3e6, mode='cont', Bethe_model='classical',
+              maxScatt=100000, Wc=10., elastic=elastic)
+    els = o.run_electrons(ip, 0, 6, 12345)
+    _check_traj(g, els, ['pathl', 'E_loss', 'pol_angle', 'az_angle', 'energy', 'direction'], atol=1e-8)
+    assert els[0].scats[0]['type'] == elastic          # scattering.py:834
+
+
 def test_philox_known_answer():
     """Random123 known-answer vectors for Philox4x32-10."""
     assert o.philox4x32_10((0, 0, 0, 0), (0, 0)) == (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)
