@@ -205,6 +205,22 @@ int mcd_drain_scats(mcd_ctx* ctx, uint32_t* host_words, uint64_t offset, uint64_
 int mcd_order_scats(mcd_ctx* ctx, void* stream);
 int mcd_drain_scats_ordered(mcd_ctx* ctx, uint32_t* host_words, uint64_t offset, uint64_t n, void* stream);
 int mcd_scat_offsets(mcd_ctx* ctx, uint64_t* host, uint64_t first, uint64_t n, void* stream);
+/* Columnar variant of the same regrouping (what the reference's listener finally stores is columns:
+ * pd.DataFrame.from_dict(results_d[key]), doScatter.py:112-117): every payload word of a row becomes one float32
+ * column and the channel index one uint8 column, all in trajectory order; the electron id and event index words
+ * are not stored (they follow from mcd_scat_offsets), so a `type, position, energy` row costs 17 bytes of D2H
+ * traffic instead of 24.  Layout of the block copied by mcd_drain_scats_columns: float column j (= row word 2+j of
+ * mcd_scat_layout) at byte offset j * col_stride, the uint8 channel column at type_offset; n_rows entries each. */
+int mcd_order_scats_columns(mcd_ctx* ctx, void* stream);
+/* The same regrouping ENQUEUED on `stream` right behind mcd_run, with no host synchronisation (the used chunk count
+ * is read on the device, the columns are laid out for the capacity of the chunk pool): in a pipelined run the
+ * regrouping of batch k+1 then overlaps the D2H drain of batch k.  Synchronise the stream before calling
+ * mcd_scat_columns_layout / mcd_drain_scats_columns / mcd_scat_offsets, which verify the result (no dropped rows,
+ * event counts == stored rows) on first use. */
+int mcd_order_scats_columns_enqueue(mcd_ctx* ctx, void* stream);
+int mcd_scat_columns_layout(mcd_ctx* ctx, uint64_t* n_rows, uint64_t* n_float_cols, uint64_t* col_stride,
+                            uint64_t* type_offset, uint64_t* total_bytes);
+int mcd_drain_scats_columns(mcd_ctx* ctx, void* host, uint64_t capacity_bytes, void* stream);
 int mcd_counters_get(mcd_ctx* ctx, mcd_counters* out);
 int mcd_hist_get(mcd_ctx* ctx, int64_t* host /* MCD_HIST_TOTAL */);
 /* Device address of the int64 histogram||counter block, for an in-place NCCL all-reduce by the caller

@@ -85,6 +85,10 @@ SYMBOLS = {
     'mcd_order_scats': (C.c_int, [_P, _P]),
     'mcd_drain_scats_ordered': (C.c_int, [_P, _P, _U64, _U64, _P]),
     'mcd_scat_offsets': (C.c_int, [_P, C.POINTER(_U64), _U64, _U64, _P]),
+    'mcd_order_scats_columns': (C.c_int, [_P, _P]),
+    'mcd_order_scats_columns_enqueue': (C.c_int, [_P, _P]),
+    'mcd_scat_columns_layout': (C.c_int, [_P] + [C.POINTER(_U64)] * 5),
+    'mcd_drain_scats_columns': (C.c_int, [_P, _P, _U64, _P]),
     'mcd_counters_get': (C.c_int, [_P, C.POINTER(Counters)]),
     'mcd_hist_get': (C.c_int, [_P, C.POINTER(C.c_int64)]),
     'mcd_stats_device_ptr': (C.c_int, [_P, C.POINTER(_P), C.POINTER(_U64)]),

@@ -58,7 +58,9 @@ struct mcd_ctx {
   unsigned long long* offsets = nullptr;      // max_el + 1
   unsigned long long* tile_tmp = nullptr;
   unsigned long long* total_dev = nullptr;
-  bool ordered = false;
+  int ordered = 0;                            // 0 no, 1 rows (mcd_order_scats), 2 columns (mcd_order_scats_columns),
+                                              // 3 columns enqueued behind the run, not yet verified
+  uint64_t col_stride = 0;                    // bytes between the float columns of the columnar layout ON THE DEVICE
   unsigned long long* ticket = nullptr;       // 8 words: [0..3] id tickets of the passes, [4..6] leftover counts
   uint32_t* rq[2] = {nullptr, nullptr};       // leftover queues of the tail hand-over (statistics-only DS runs)
   unsigned int rq_cap = 0;
@@ -789,7 +791,7 @@ int mcd_run(mcd_ctx* c, uint64_t first_id, uint64_t count, void* stream) {
   CU(c, cudaEventRecord(c->ev1, s));
   c->last_count = count;
   c->seg_cached = false;
-  c->ordered = false;
+  c->ordered = 0;
   c->timed = true;
   return MCD_OK;
 }
@@ -871,7 +873,7 @@ int mcd_drain_scats(mcd_ctx* c, uint32_t* host, uint64_t offset, uint64_t n, voi
   return MCD_OK;
 }
 
-int mcd_order_scats(mcd_ctx* c, void* stream) {
+static int order_impl(mcd_ctx* c, void* stream, bool columns) {
   int rc = need_ctx(c);
   if (rc) return rc;
   if (!c->scats || !c->nev || !c->last_count) return fail(c, MCD_ERR_STATE, "no scats rows to order");
@@ -896,22 +898,112 @@ int mcd_order_scats(mcd_ctx* c, void* stream) {
   unsigned int used = 0;
   CU(c, cudaMemcpy(&used, c->chunk_next, sizeof used, cudaMemcpyDeviceToHost));
   if (used > c->n_chunks) used = c->n_chunks;
+  // columnar layout: (row_words - 2) float columns of rows_total entries, each starting on a 256-byte boundary,
+  // then the channel bytes; it always fits the row-major buffer (4 (rw-2) + 1 < 4 rw bytes per row, +1024 rows slack)
+  c->col_stride = columns ? ((c->rows_total * 4 + 255) / 256) * 256 : 0;
+  if (columns && c->P.scat_row_words < 2) return fail(c, MCD_ERR_STATE, "no scats columns");
   CU(c, mcd_launch_order_scats(c->nev, c->last_count, c->tile_tmp, c->offsets, c->total_dev, c->scats, c->chunk_count,
-                               used, c->P.scat_row_words, c->sorted, c->sm_count, s));
+                               used, c->P.scat_row_words, c->sorted, c->col_stride, nullptr, c->sm_count, s));
   unsigned long long total = 0;
   CU(c, cudaMemcpyAsync(&total, c->total_dev, sizeof total, cudaMemcpyDeviceToHost, s));
   CU(c, cudaStreamSynchronize(s));
   if (total != c->rows_total)
     return fail(c, MCD_ERR_STATE, "event counts (%llu) and stored rows (%llu) disagree", total,
                 (unsigned long long)c->rows_total);
-  c->ordered = true;
+  c->ordered = columns ? 2 : 1;
+  return MCD_OK;
+}
+
+int mcd_order_scats(mcd_ctx* c, void* stream) { return order_impl(c, stream, false); }
+int mcd_order_scats_columns(mcd_ctx* c, void* stream) { return order_impl(c, stream, true); }
+
+int mcd_order_scats_columns_enqueue(mcd_ctx* c, void* stream) {
+  int rc = need_ctx(c);
+  if (rc) return rc;
+  if (!c->scats || !c->nev || !c->last_count) return fail(c, MCD_ERR_STATE, "no scats rows to order");
+  if (c->P.scat_row_words < 2) return fail(c, MCD_ERR_STATE, "no scats columns");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!c->offsets) {
+    CU(c, cudaMalloc(&c->offsets, (c->max_el + 1) * sizeof(unsigned long long)));
+    CU(c, cudaMalloc(&c->tile_tmp, mcd_order_tiles(c->max_el) * sizeof(unsigned long long)));
+    CU(c, cudaMalloc(&c->total_dev, sizeof(unsigned long long)));
+  }
+  // the row count is not known on the host yet: columns are laid out for the capacity of the chunk pool
+  const uint64_t rw = (uint64_t)c->P.scat_row_words;
+  const uint64_t cap_rows = (uint64_t)c->n_chunks * MCD_CHUNK_ROWS;
+  const uint64_t stride = ((cap_rows * 4 + 255) / 256) * 256;
+  const uint64_t need_rows = ((rw - 2) * stride + cap_rows + rw * 4 - 1) / (rw * 4);
+  if (c->sorted_cap_rows < need_rows) {
+    cudaFree(c->sorted); c->sorted = nullptr; c->sorted_cap_rows = 0;
+    CU(c, cudaMalloc(&c->sorted, need_rows * rw * 4));
+    c->sorted_cap_rows = need_rows;
+  }
+  c->col_stride = stride;
+  CU(c, mcd_launch_order_scats(c->nev, c->last_count, c->tile_tmp, c->offsets, c->total_dev, c->scats, c->chunk_count,
+                               c->n_chunks, c->P.scat_row_words, c->sorted, c->col_stride, c->chunk_next, c->sm_count, s));
+  c->ordered = 3;
+  return MCD_OK;
+}
+
+// An enqueued regrouping is checked on first use (the caller has synchronised the stream by then).
+static int columns_ready(mcd_ctx* c) {
+  if (c->ordered == 2) return MCD_OK;
+  if (c->ordered != 3) return fail(c, MCD_ERR_STATE, "mcd_order_scats_columns has not been called for the last run");
+  mcd_counters cn;
+  unsigned long long total = 0;
+  CU(c, cudaMemcpy(&cn, c->stats + MCD_HIST_TOTAL, sizeof cn, cudaMemcpyDeviceToHost));
+  CU(c, cudaMemcpy(&total, c->total_dev, sizeof total, cudaMemcpyDeviceToHost));
+  if (cn.scat_rows_dropped) return fail(c, MCD_ERR_OVERFLOW, "rows were dropped: cannot regroup an incomplete run");
+  if (total != (unsigned long long)cn.scat_rows_stored)
+    return fail(c, MCD_ERR_STATE, "event counts (%llu) and stored rows (%llu) disagree", total,
+                (unsigned long long)cn.scat_rows_stored);
+  c->rows_total = (uint64_t)cn.scat_rows_stored;
+  c->ordered = 2;
+  return MCD_OK;
+}
+
+// host layout of the drained block: columns packed for the actual row count
+int mcd_scat_columns_layout(mcd_ctx* c, uint64_t* n_rows, uint64_t* n_float_cols, uint64_t* col_stride,
+                            uint64_t* type_offset, uint64_t* total_bytes) {
+  int rc = need_ctx(c);
+  if (rc) return rc;
+  rc = columns_ready(c);
+  if (rc) return rc;
+  const uint64_t nf = (uint64_t)c->P.scat_row_words - 2;
+  const uint64_t hs = ((c->rows_total * 4 + 255) / 256) * 256;
+  if (n_rows) *n_rows = c->rows_total;
+  if (n_float_cols) *n_float_cols = nf;
+  if (col_stride) *col_stride = hs;
+  if (type_offset) *type_offset = nf * hs;
+  if (total_bytes) *total_bytes = nf * hs + c->rows_total;
+  return MCD_OK;
+}
+
+int mcd_drain_scats_columns(mcd_ctx* c, void* host, uint64_t capacity_bytes, void* stream) {
+  int rc = need_ctx(c);
+  if (rc) return rc;
+  rc = columns_ready(c);
+  if (rc) return rc;
+  const uint64_t nf = (uint64_t)c->P.scat_row_words - 2, n = c->rows_total;
+  const uint64_t hs = ((n * 4 + 255) / 256) * 256;
+  if (!host || capacity_bytes < nf * hs + n) return fail(c, MCD_ERR_INVALID, "host buffer smaller than the column block");
+  if (!n) return MCD_OK;
+  const unsigned char* dev = reinterpret_cast<const unsigned char*>(c->sorted);
+  unsigned char* h = static_cast<unsigned char*>(host);
+  if (hs == c->col_stride) {                                          // device layout == host layout: one copy
+    CU(c, cudaMemcpyAsync(h, dev, nf * hs + n, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return MCD_OK;
+  }
+  for (uint64_t j = 0; j < nf; ++j)
+    CU(c, cudaMemcpyAsync(h + j * hs, dev + j * c->col_stride, n * 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CU(c, cudaMemcpyAsync(h + nf * hs, dev + nf * c->col_stride, n, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   return MCD_OK;
 }
 
 int mcd_drain_scats_ordered(mcd_ctx* c, uint32_t* host, uint64_t offset, uint64_t n, void* stream) {
   int rc = need_ctx(c);
   if (rc) return rc;
-  if (!c->ordered) return fail(c, MCD_ERR_STATE, "mcd_order_scats has not been called for the last run");
+  if (c->ordered != 1) return fail(c, MCD_ERR_STATE, "mcd_order_scats has not been called for the last run");
   if (!host || offset + n > c->rows_total) return fail(c, MCD_ERR_INVALID, "scats range outside the stored rows");
   const uint64_t rw = (uint64_t)c->P.scat_row_words;
   if (n) CU(c, cudaMemcpyAsync(host, c->sorted + offset * rw, n * rw * 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
@@ -921,6 +1013,10 @@ int mcd_drain_scats_ordered(mcd_ctx* c, uint32_t* host, uint64_t offset, uint64_
 int mcd_scat_offsets(mcd_ctx* c, uint64_t* host, uint64_t first, uint64_t n, void* stream) {
   int rc = need_ctx(c);
   if (rc) return rc;
+  if (c->ordered == 3) {
+    rc = columns_ready(c);
+    if (rc) return rc;
+  }
   if (!c->ordered) return fail(c, MCD_ERR_STATE, "mcd_order_scats has not been called for the last run");
   if (!host || first + n > c->last_count) return fail(c, MCD_ERR_INVALID, "offset range outside the last run");
   CU(c, cudaMemcpyAsync(host, c->offsets + first, (n + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost,

@@ -724,12 +724,53 @@ __global__ void __launch_bounds__(256) scatter_rows(const uint32_t* __restrict__
   }
 }
 
+// Columnar variant: the payload words 2.. of every row go to one float column each (column j = word 2+j at byte
+// offset j * col_stride) and the channel index to a byte column; row d of every column = the event offsets[rel_id] +
+// event.  Words 0/1 (electron id, event index) are NOT stored: in trajectory order they follow from the offsets.
+__global__ void __launch_bounds__(256) scatter_cols(const uint32_t* __restrict__ pool,
+                                                    const unsigned int* __restrict__ chunk_count, unsigned int nchunks,
+                                                    int row_words, const unsigned long long* __restrict__ offsets,
+                                                    unsigned char* __restrict__ cols, unsigned long long col_stride,
+                                                    const unsigned int* __restrict__ nchunks_dev) {
+  // enqueued right behind the trajectory kernel (no host round trip): the number of used chunks is still on the device
+  if (nchunks_dev) nchunks = min(nchunks, *nchunks_dev);
+  unsigned char* type_col = cols + (unsigned long long)(row_words - 2) * col_stride;
+  for (unsigned int c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    const unsigned int cnt = chunk_count[c];
+    const uint32_t* cbase = pool + (size_t)c * MCD_CHUNK_ROWS * (size_t)row_words;
+    if ((row_words & 1) == 0) {
+      const int rw2 = row_words >> 1;
+      for (unsigned int r = threadIdx.x; r < cnt; r += blockDim.x) {
+        const uint2* src = reinterpret_cast<const uint2*>(cbase) + (size_t)r * rw2;
+        const uint2 head = __ldcs(src);
+        const unsigned long long d = offsets[head.x] + (unsigned long long)(head.y & 0xffffffu);
+        type_col[d] = (unsigned char)(head.y >> 24);
+        for (int w = 1; w < rw2; ++w) {
+          const uint2 v = __ldcs(src + w);
+          reinterpret_cast<uint32_t*>(cols + (unsigned long long)(2 * w - 2) * col_stride)[d] = v.x;
+          reinterpret_cast<uint32_t*>(cols + (unsigned long long)(2 * w - 1) * col_stride)[d] = v.y;
+        }
+      }
+    } else {
+      for (unsigned int r = threadIdx.x; r < cnt; r += blockDim.x) {
+        const uint32_t* src = cbase + (size_t)r * row_words;
+        const uint32_t rel = src[0], w1 = src[1];
+        const unsigned long long d = offsets[rel] + (unsigned long long)(w1 & 0xffffffu);
+        type_col[d] = (unsigned char)(w1 >> 24);
+        for (int w = 2; w < row_words; ++w)
+          reinterpret_cast<uint32_t*>(cols + (unsigned long long)(w - 2) * col_stride)[d] = src[w];
+      }
+    }
+  }
+}
+
 }  // namespace
 
 cudaError_t mcd_launch_order_scats(const unsigned int* nev, unsigned long long count, unsigned long long* tile_tmp,
                                    unsigned long long* offsets, unsigned long long* total_dev, const uint32_t* pool,
                                    const unsigned int* chunk_count, unsigned int nchunks, int row_words,
-                                   uint32_t* sorted, int sm_count, cudaStream_t stream) {
+                                   uint32_t* sorted, unsigned long long col_stride, const unsigned int* nchunks_dev,
+                                   int sm_count, cudaStream_t stream) {
   const unsigned long long per_tile = (unsigned long long)kScanT * kScanItems;
   const unsigned int ntiles = (unsigned int)((count + 1 + per_tile - 1) / per_tile);
   scan_tile_sums<<<ntiles, kScanT, 0, stream>>>(nev, count, tile_tmp);
@@ -737,7 +778,11 @@ cudaError_t mcd_launch_order_scats(const unsigned int* nev, unsigned long long c
   scan_apply<<<ntiles, kScanT, 0, stream>>>(nev, count, tile_tmp, offsets);
   if (sorted && nchunks) {
     const unsigned int grid = nchunks < (unsigned int)(sm_count * 64) ? nchunks : (unsigned int)(sm_count * 64);
-    scatter_rows<<<grid, 256, 0, stream>>>(pool, chunk_count, nchunks, row_words, offsets, sorted);
+    if (col_stride)
+      scatter_cols<<<grid, 256, 0, stream>>>(pool, chunk_count, nchunks, row_words, offsets,
+                                             reinterpret_cast<unsigned char*>(sorted), col_stride, nchunks_dev);
+    else
+      scatter_rows<<<grid, 256, 0, stream>>>(pool, chunk_count, nchunks, row_words, offsets, sorted);
   }
   return cudaGetLastError();
 }

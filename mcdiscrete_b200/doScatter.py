@@ -70,7 +70,7 @@ def main(argv=None):
     with ResultStore(path, inputPar, fmt) as st:
         for first in range(lo, lo + n, batch):
             cnt = min(batch, lo + n - first)
-            res = eng.run(count=cnt, first_id=first, pinned=True, ordered=True)
+            res = eng.run(count=cnt, first_id=first, pinned=True, ordered='columns')
             events += res.counters['events']
             st.append_result(res, names, double_record=bool(inputPar.get('reference_double_record', False)))
             s = eng.stats_tensor().clone()

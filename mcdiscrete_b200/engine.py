@@ -83,6 +83,65 @@ class ScatRows:
         return v
 
 
+class ScatCols:
+    """scats rows drained COLUMN by column in trajectory order (mcd_order_scats_columns): same dict-like interface
+    as ScatRows, but every float column is a contiguous float32 array and 'type' a contiguous int8 array -- what
+    the reference finally stores (DataFrame columns, doScatter.py:112-117).  'el' and 'ev' are not transferred;
+    they are rebuilt from `offsets` (electron i owns rows offsets[i]:offsets[i+1]) on first use."""
+
+    def __init__(self, block, n_rows, col_stride, type_offset, word_of, first_id, offsets):
+        self.block, self.n, self.word_of, self.first_id, self.offsets = block, int(n_rows), word_of, int(first_id), offsets
+        self._stride, self._type_off = int(col_stride), int(type_offset)
+        self._cache = {}
+        self._names = ['el', 'ev']
+        if word_of[0] >= 0:
+            self._names.append('type')
+        for b, nm in ScatRows._FLOAT.items():
+            if word_of[b] >= 0:
+                self._names += ['x', 'y', 'z'] if nm == 'position' else [nm]
+
+    def __len__(self):
+        return self.n
+
+    def __bool__(self):
+        return True
+
+    def keys(self):
+        return list(self._names)
+
+    def __contains__(self, k):
+        return k in self._names
+
+    def items(self):
+        return [(k, self[k]) for k in self._names]
+
+    def _word(self, w):
+        a = (w - 2) * self._stride
+        return self.block[a:a + 4 * self.n].view(np.float32)
+
+    def __getitem__(self, k):
+        if k in self._cache:
+            return self._cache[k]
+        if k not in self._names:
+            raise KeyError(k)
+        if k in ('el', 'ev'):
+            off = np.asarray(self.offsets, np.int64)
+            nev = np.diff(off)
+            el = np.repeat(np.arange(len(nev), dtype=np.int64), nev)
+            v = el + self.first_id if k == 'el' else (np.arange(self.n, dtype=np.int64) - off[:-1][el]).astype(np.int32)
+        elif k == 'type':
+            v = self.block[self._type_off:self._type_off + self.n].view(np.int8)
+        elif k in ('x', 'y', 'z'):
+            v = self._word(self.word_of[1] + 'xyz'.index(k))
+        elif k == 'direction':
+            v = np.stack([self._word(self.word_of[8] + i) for i in range(3)], 1)
+        else:
+            b = [b for b, nm in ScatRows._FLOAT.items() if nm == k][0]
+            v = self._word(self.word_of[b])
+        self._cache[k] = v
+        return v
+
+
 class RunResult:
     """Columnar output of one run.
 
@@ -186,6 +245,7 @@ class Engine:
         self.row_words = int(lay.row_words)
         self.word_of = list(lay.word_of)
         self.tables = None
+        self._order_enqueued = False
         self.cap_el = self.cap_sc = 0
         self.next_id = 0
         self._pinned = {}
@@ -328,7 +388,9 @@ class Engine:
 
     def drain(self, first_id, count, want_els=True, want_scats=True, pinned=False, stream=None, ordered=False):
         """Copy the rows of the last run to host arrays.  ordered=True regroups the scats rows on the device
-        into trajectory order first (mcd_order_scats) and returns them with per-electron offsets."""
+        into trajectory order first (mcd_order_scats) and returns them with per-electron offsets;
+        ordered='columns' does the same regrouping into one contiguous array per column (ScatCols) and leaves
+        the id / event words on the device (17 instead of 24 bytes per `type, position, energy` row)."""
         st = C.c_void_p(stream or 0)
         n_els, n_sc = C.c_uint64(), C.c_uint64()
         self._ck(self.lib.mcd_row_counts(self.ctx, C.byref(n_els), C.byref(n_sc)))
@@ -341,8 +403,21 @@ class Engine:
         nsc = int(n_sc.value)
         words = None
         if want_scats and self.row_words and self.cap_sc:
-            rawb = self._host('scats', nsc * self.row_words * 4, pinned)
             offs = None
+            if nsc and ordered == 'columns':
+                if not self._order_enqueued:
+                    self._ck(self.lib.mcd_order_scats_columns(self.ctx, st))
+                self._order_enqueued = False
+                lay = [C.c_uint64() for _ in range(5)]
+                self._ck(self.lib.mcd_scat_columns_layout(self.ctx, *[C.byref(v) for v in lay]))
+                n_rows, _, stride, type_off, total = [int(v.value) for v in lay]
+                block = self._host('scats', total, pinned)
+                self._ck(self.lib.mcd_drain_scats_columns(self.ctx, block.ctypes.data_as(C.c_void_p), total, st))
+                offs = self._host('offsets', (count + 1) * 8, pinned).view(np.uint64)
+                self._ck(self.lib.mcd_scat_offsets(self.ctx, offs.ctypes.data_as(C.POINTER(C.c_uint64)), 0, count, st))
+                self.sync(stream)
+                return els, ScatCols(block, n_rows, stride, type_off, self.word_of, first_id, offs)
+            rawb = self._host('scats', nsc * self.row_words * 4, pinned)
             if nsc and ordered:
                 self._ck(self.lib.mcd_order_scats(self.ctx, st))
                 self._ck(self.lib.mcd_drain_scats_ordered(self.ctx, rawb.ctypes.data_as(C.c_void_p), 0, nsc, st))
@@ -440,6 +515,10 @@ class Engine:
                 e.set_capacity(max(batch, e.cap_el), max(max_scat_rows, e.cap_sc))
                 e.reset_stats(st)
                 e.launch(first, cnt, st)
+                if ordered == 'columns' and e.row_words:
+                    # regrouping enqueued behind the kernel: it overlaps the D2H drain of the previous batch
+                    e._ck(e.lib.mcd_order_scats_columns_enqueue(e.ctx, st))
+                    e._order_enqueued = True
                 if on_launched is not None:
                     with torch.cuda.stream(streams[k % depth]):
                         on_launched(e, streams[k % depth])

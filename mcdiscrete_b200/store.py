@@ -3,13 +3,17 @@
   'els'    one row per saveOutcomes call, columns in zipDict order (fileTools.py:67-99),
   'scats'  one row per scattering event.
 
-Two back ends with the same keys, column names, order and dtypes (float64 / str):
-  * HDF5 through pandas.HDFStore (PyTables 'table' format, data_columns=True, appendable) -- exactly what the
-    reference writes -- when PyTables is importable;
-  * a directory of Parquet files (pyarrow) otherwise.  This image ships no HDF5 library (no PyTables, h5py or
-    libhdf5), so Parquet is what runs here; `fmt='auto'` picks HDF5 wherever it is available.
-Rows are appended in batches straight from the columnar GPU output: the per-4-electron open/append/close cycle
-that made the reference lock up above 5e5 electrons (README.md:58-59) does not exist.
+Three back ends with the same keys, column names, order and dtypes (float64 / str):
+  * 'hdf5' with PyTables importable: pandas.HDFStore (PyTables 'table' format, data_columns=True, appendable) --
+    exactly what the reference writes;
+  * 'hdf5' without PyTables (this image ships no HDF5 library at all): the self-contained writer
+    mcdiscrete_b200/h5lite.py produces the same file layout -- groups /input, /els, /scats, each holding a chunked,
+    unlimited-length compound dataset `table` (int64 `index` + one field per column) with the PyTables and pandas
+    attributes of an appendable frame table.  Columns go from the GPU's arrays straight into the compound rows (no
+    DataFrame, no per-row Python objects); chunks stream to disk as batches arrive;
+  * 'parquet': a directory of Parquet files (pyarrow).
+`fmt='auto'` = 'hdf5'.  Rows are appended in batches straight from the columnar GPU output: the per-4-electron
+open/append/close cycle that made the reference lock up above 5e5 electrons (README.md:58-59) does not exist.
 """
 import json
 import os
@@ -90,17 +94,125 @@ def scats_frame(res, inputPar, channel_names, sort=True):
     return pd.DataFrame(data, columns=out_cols)
 
 
+STR_WIDTH = 16       # longest labels: 'Gryz3s3p3d', 'Ruth_nigram_wDefl' (the reference's min_itemsize=6 truncates them)
+
+
+def els_columns(res, inputPar, double_record=False):
+    """els rows as {column: array} in the reference's column order; 'outcome' as fixed-width byte strings."""
+    cols = flat_columns(inputPar['electron_output'], 'els')
+    e = res.els
+    idx = np.arange(len(e))
+    second = None
+    if double_record:                      # SURVEY Q4: the reference appends a second 'abs' row
+        idx = np.sort(np.concatenate([idx, idx[(e['code'] & 0x100) != 0]]))
+        second = np.zeros(len(idx), bool)
+        second[1:] = idx[1:] == idx[:-1]
+    out = {}
+    for c in cols:
+        if c == 'outcome':
+            names = np.array(_lib.OUTCOMES, dtype='S%d' % STR_WIDTH)[(e['code'][idx] & 0xff)]
+            if second is not None:
+                names[second] = b'abs'
+            out[c] = names
+        else:
+            out[c] = e[c][idx].astype(np.float64)
+    return out
+
+
+def scats_columns(res, inputPar, channel_names, sort=True):
+    """scats rows as {column: array}: scalar columns in requested order, then x, y, z (zipDict order)."""
+    sc = res.sorted_scats() if sort else res.scats
+    cont = 'DS' not in inputPar['mode']
+    req = [c for c in inputPar['scatter_output'] if not (cont and c in ('position', 'E'))]
+    out = {}
+    for c in flat_columns(req, 'scats'):
+        if c == 'type':
+            if cont:
+                out[c] = np.full(len(sc), inputPar.get('elastic', 'Ruth_vanilla').encode(), dtype='S%d' % STR_WIDTH)
+            else:
+                out[c] = np.array(channel_names, dtype='S%d' % STR_WIDTH)[sc['type']]
+        elif c == 'direction':
+            d = sc['direction']
+            for k, nm in enumerate(('dir_x', 'dir_y', 'dir_z')):
+                out[nm] = d[:, k].astype(np.float64)
+        else:
+            out[c] = np.asarray(sc[c], dtype=np.float64)
+    return out
+
+
+class _H5LiteTable:
+    """One pandas-style appendable frame table (`/key/table`) written through h5lite."""
+
+    def __init__(self, writer, key, cols, chunk_rows):
+        self.w, self.key = writer, key
+        self.names = list(cols)
+        self.dtype = np.dtype([('index', '<i8')] + [(n, cols[n].dtype.newbyteorder('<') if cols[n].dtype.kind != 'S'
+                                                     else cols[n].dtype) for n in self.names])
+        self.table = writer.create_table('/%s/table' % key, self.dtype, chunk_rows)
+        self.rows = 0
+
+    def append(self, cols):
+        n = len(next(iter(cols.values()))) if cols else 0
+        if list(cols) != self.names:
+            raise ValueError('columns %s do not match the table %s' % (list(cols), self.names))
+        step = 1 << 20                       # build the compound rows in slices: bounded extra host memory
+        for a in range(0, n, step):
+            b = min(n, a + step)
+            rows = np.empty(b - a, self.dtype)
+            rows['index'] = np.arange(self.rows + a, self.rows + b)
+            for k in self.names:
+                rows[k] = cols[k][a:b]
+            self.w.append(self.table, rows)
+        self.rows += n
+
+    def finish(self):
+        names = self.names
+        self.w.set_attrs('/' + self.key, {
+            'CLASS': 'GROUP', 'TITLE': '', 'VERSION': '1.0', 'pandas_type': 'frame_table',
+            'pandas_version': '0.15.2', 'table_type': 'appendable_frame', 'index_cols': [(0, 'index')],
+            'values_cols': list(names), 'non_index_axes': [(1, list(names))], 'data_columns': list(names),
+            'nan_rep': 'nan', 'encoding': 'UTF-8', 'errors': 'strict', 'levels': 1, 'metadata': [],
+            'info': {1: {'type': 'Index', 'names': [None]}, 'index': {}}})
+        at = {'CLASS': 'TABLE', 'VERSION': '2.7', 'TITLE': '', 'NROWS': np.int64(self.rows), 'index_kind': 'integer'}
+        for i, n in enumerate(self.dtype.names):
+            sub = self.dtype.fields[n][0]
+            at['FIELD_%d_NAME' % i] = n
+            at['FIELD_%d_FILL' % i] = b'' if sub.kind == 'S' else np.zeros((), sub)[()]
+        for n in names:
+            sub = self.dtype.fields[n][0]
+            at[n + '_kind'] = [n]
+            at[n + '_meta'] = None
+            at[n + '_dtype'] = sub.name              # 'float64', 'bytes128'
+        self.w.set_attrs('/%s/table' % self.key, at)
+
+
 class ResultStore:
     """Appendable store; use as a context manager."""
 
-    def __init__(self, path, inputPar, fmt='auto'):
-        import pandas as pd
+    def __init__(self, path, inputPar, fmt='auto', chunk_rows=1 << 18):
         self.inputPar = dict(inputPar)
         if fmt == 'auto':
-            fmt = 'hdf5' if have_pytables() else 'parquet'
+            fmt = 'hdf5'
         self.fmt = fmt
         self.path = path
         self._pq = {}
+        self._h5 = None
+        if fmt == 'hdf5' and not have_pytables():
+            from . import h5lite
+            if os.path.exists(path):
+                os.remove(path)
+            self.fmt = 'h5lite'
+            self._h5 = h5lite.Writer(path)
+            self._h5.set_attrs('/', {'CLASS': 'GROUP', 'PYTABLES_FORMAT_VERSION': '2.1', 'TITLE': '', 'VERSION': '1.0'})
+            self._h5_tables = {}
+            self._chunk_rows = int(chunk_rows)
+            # doScatter.py:201-203: store['input'] = one-row frame of the parameters (here: as strings)
+            vals = {str(k): np.array([str(v).encode()]) for k, v in self.inputPar.items()}
+            t = _H5LiteTable(self._h5, 'input', vals, 1)
+            t.append(vals)
+            self._h5_tables['input'] = t
+            return
+        import pandas as pd
         ser = pd.Series([str(v) for v in self.inputPar.values()], index=list(self.inputPar.keys()), dtype=str)
         if fmt == 'hdf5':
             if os.path.exists(path):
@@ -119,6 +231,11 @@ class ResultStore:
     def append(self, key, df):
         if len(df) == 0:
             return
+        if self.fmt == 'h5lite':
+            self.append_columns(key, {c: (np.asarray(df[c].astype(str).str.encode('utf-8'), dtype='S%d' % STR_WIDTH)
+                                          if df[c].dtype == object or str(df[c].dtype).startswith('str')
+                                          else np.asarray(df[c])) for c in df.columns})
+            return
         if self.fmt == 'hdf5':
             # widths of the longest labels (the reference's min_itemsize=6 truncates 'Gryz2s2p', doScatter.py:75-79)
             sizes = {c: 16 for c in df.columns if df[c].dtype == object}
@@ -132,12 +249,31 @@ class ResultStore:
                 w = self._pq[key] = pq.ParquetWriter(os.path.join(self.path, key + '.parquet'), tab.schema)
             w.write_table(tab)
 
+    def append_columns(self, key, cols):
+        """h5lite back end: {column: array} -> compound rows of /key/table."""
+        t = self._h5_tables.get(key)
+        if t is None:
+            t = self._h5_tables[key] = _H5LiteTable(self._h5, key, cols, self._chunk_rows)
+        t.append(cols)
+
     def append_result(self, res, channel_names, double_record=False):
+        if self.fmt == 'h5lite':
+            self.append_columns('els', els_columns(res, self.inputPar, double_record))
+            if len(res.scats):
+                self.append_columns('scats', scats_columns(res, self.inputPar, channel_names))
+            return
         self.append('els', els_frame(res, self.inputPar, double_record))
         if len(res.scats):
             self.append('scats', scats_frame(res, self.inputPar, channel_names))
 
     def close(self):
+        if self.fmt == 'h5lite':
+            if self._h5 is not None:
+                for t in self._h5_tables.values():
+                    t.finish()
+                self._h5.close()
+                self._h5 = None
+            return
         if self.fmt == 'hdf5':
             self.store.close()
         for w in self._pq.values():
@@ -161,5 +297,31 @@ def read_store(path):
             f = os.path.join(path, key + '.parquet')
             out[key] = pd.read_parquet(f) if os.path.exists(f) else None
         return out
+    if not have_pytables():
+        return read_store_h5lite(path)
     with pd.HDFStore(path, mode='r') as st:
         return {'input': st['input'], 'els': st['els'], 'scats': st['scats'] if '/scats' in st.keys() else None}
+
+
+def read_frame_h5lite(f, key):
+    """/key/table of an HDF5 file (h5lite reader) -> DataFrame, the way pandas.read_hdf returns a frame table."""
+    import pandas as pd
+    g = f[key]
+    if g.attr('pandas_type') != 'frame_table':
+        raise ValueError('%s is not a pandas frame table' % key)
+    rows = g['table'].read()
+    cols = g.attr('non_index_axes')[0][1]
+    data = {}
+    for c in cols:
+        v = rows[c]
+        data[c] = np.char.decode(v, g.attr('encoding')).astype(object) if v.dtype.kind == 'S' else np.ascontiguousarray(v)
+    return pd.DataFrame(data, columns=cols, index=pd.Index(np.ascontiguousarray(rows['index'])))
+
+
+def read_store_h5lite(path):
+    from . import h5lite
+    with h5lite.File(path) as f:
+        inp = read_frame_h5lite(f, 'input')
+        out = {'input': inp.iloc[0], 'els': read_frame_h5lite(f, 'els') if 'els' in f else None}
+        out['scats'] = read_frame_h5lite(f, 'scats') if 'scats' in f else None
+    return out

@@ -62,27 +62,28 @@ def run(tag, ip, n, batch=None, scats=False, reps=2):
     eng.close()
 
 
-def run_pipelined(tag, ip, total, batch):
+def run_pipelined(tag, ip, total, batch, ordered=True):
     """Full scatter_output through the pipelined public API: kernel k+1 overlaps the D2H drain of batch k; rows
     arrive on the host already regrouped per electron (device-side scan + scatter)."""
     import torch
     eng = Engine(ip, device=0)
     genTables(ip, engine=eng)
-    for r in eng.run_batches(2 * batch, batch, first_id=10 ** 10, ordered=True):      # warm-up: pin staging buffers
+    for r in eng.run_batches(2 * batch, batch, first_id=10 ** 10, ordered=ordered):   # warm-up: pin staging buffers
         pass
     torch.cuda.synchronize()
     t0 = time.time()
     rows = ev = 0
     kms = 0.0
-    for r in eng.run_batches(total, batch, first_id=0, ordered=True):
+    for r in eng.run_batches(total, batch, first_id=0, ordered=ordered):
         rows += len(r.scats)
         ev += r.counters['events']
         kms += r.kernel_ms
         _ = float(r.scats['energy'][-1]) + int(r.scats.offsets[-1])
     wall = time.time() - t0
-    nbytes = rows * eng.row_words * 4 + total * 32
+    row_bytes = eng.row_words * 4 if ordered is True else (eng.row_words - 2) * 4 + 1
+    nbytes = rows * row_bytes + total * 32 + (total + 1) * 8
     print(json.dumps(dict(config=tag, material=ip['material'], electrons=total, batch=batch, scats_rows=rows,
-                          row_bytes=eng.row_words * 4, e2e_electrons_per_s=total / wall, e2e_rows_per_s=rows / wall,
+                          row_bytes=row_bytes, e2e_electrons_per_s=total / wall, e2e_rows_per_s=rows / wall,
                           e2e_GBps_to_host=nbytes / 1e9 / wall, kernel_events_per_s=ev / (kms * 1e-3),
                           wall_s=wall, kernel_s=kms * 1e-3)), flush=True)
     eng.close()
@@ -101,6 +102,8 @@ def main():
         ip = dict(BASE, material='Cu', E0=20000., Emin=10000., mode='DS', s_tilt=70., maxScatt=1000, num_el=10 ** 8,
                   scatter_output=['type', 'position', 'energy'])
         run_pipelined('C3 full scatter_output, 5e6 e- of the 1.25e7 per-GPU share, pipelined + device regroup', ip, 5000000, 1250000)
+        run_pipelined('C3 full scatter_output, 5e6 e-, pipelined + COLUMNAR device regroup (no id words)', ip, 5000000, 1250000,
+                      ordered='columns')
         ip2 = dict(ip, scatter_output=[])
         run('C3 kernel only (1e7, no scats)', ip2, 10 ** 7, reps=1)
     if 'C4' in want:   # Au 30 keV tilt 0 histograms only; Emin = E0/2, maxScatt 10000 (stated; BASELINE leaves them open)

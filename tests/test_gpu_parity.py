@@ -552,13 +552,41 @@ def test_device_regrouping_of_scats_rows():
     k = int(np.argmax(nev))
     lo, hi = int(b.scats.offsets[k]), int(b.scats.offsets[k + 1])
     assert (b.scats['el'][lo:hi] == 500 + k).all() and np.array_equal(b.scats['ev'][lo:hi], np.arange(hi - lo))
+    ref_cols = {k_: np.array(v) for k_, v in b.scats.items()}
+    # columnar regrouping (mcd_order_scats_columns): the same rows, one contiguous array per column, no id words
+    c = eng.run(count=N, first_id=500, ordered='columns')
+    assert c.sorted_scats() is c.scats and len(c.scats) == len(ref_cols['el'])
+    assert np.array_equal(c.scats.offsets, hoff)
+    assert c.scats.keys() == b.scats.keys()
+    for k_, v in ref_cols.items():
+        got = c.scats[k_]
+        assert got.dtype == v.dtype and np.array_equal(got, v), k_
+        if k_ not in ('el', 'ev', 'direction'):
+            assert got.flags['C_CONTIGUOUS']
     # pipelined batches with device regrouping
-    tot = 0
-    for r in eng.run_batches(N, 11000, first_id=500, ordered=True):
-        assert r.scats.offsets[-1] == len(r.scats)
-        tot += len(r.scats)
-    assert tot == len(b.scats)
+    for mode in (True, 'columns'):
+        tot = 0
+        for r in eng.run_batches(N, 11000, first_id=500, ordered=mode):
+            assert r.scats.offsets[-1] == len(r.scats)
+            lo_ = int(r.first_id - 500)
+            a_, b_ = int(hoff[lo_]), int(hoff[lo_ + r.count])
+            assert np.array_equal(r.scats['energy'], ref_cols['energy'][a_:b_])
+            assert np.array_equal(r.scats['type'], ref_cols['type'][a_:b_])
+            tot += len(r.scats)
+        assert tot == len(b.scats)
     eng.close()
+    # odd row length (type + energy only = 3 words) and a continuous run through the columnar path
+    for kw in (dict(scatter_output=['type', 'energy']),
+               dict(material='Al', Emin=500., mode='cont', maxScatt=100000, scatter_output=['type', 'pathl', 'direction'])):
+        e2 = make_engine(**kw)
+        if kw.get('mode') != 'cont':
+            upload_golden(e2, golden_tables('Si_15k_small'))
+        r1 = e2.run(count=5000, first_id=3, ordered=True)
+        cols1 = {k_: np.array(v) for k_, v in r1.scats.items()}
+        r2 = e2.run(count=5000, first_id=3, ordered='columns')
+        for k_, v in cols1.items():
+            assert np.array_equal(r2.scats[k_], v), k_
+        e2.close()
 
 
 @pytest.mark.parametrize('name,E0,Emin', [('Si', 20000., 10000.), ('Cu', 20000., 10000.), ('Au', 30000., 15000.),
