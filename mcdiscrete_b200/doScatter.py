@@ -56,7 +56,7 @@ def main(argv=None):
     t0 = time.time()
     genTables(inputPar, engine=eng)
     t_tab = time.time() - t0
-    use_h5 = fmt == 'hdf5' or (fmt == 'auto' and have_pytables())
+    use_h5 = fmt in ('hdf5', 'auto')          # PyTables when importable, else the self-contained writer (h5lite.py)
     path = out or store_name(inputPar, ext='.h5' if use_h5 else '.parquet')
     if world > 1:
         path += '.rank%d' % rank

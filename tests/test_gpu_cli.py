@@ -12,17 +12,20 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_cli_writes_reference_layout(tmp_path):
+@pytest.mark.parametrize('fmt', ['parquet', 'hdf5'])
+def test_cli_writes_reference_layout(tmp_path, fmt):
     inp = tmp_path / 'input.file'
     inp.write_text('\n'.join([
         'num_el : 3000', 'E0 : 20000 # eV', 'Emin : 15000', 'material : Si', 's_tilt : 70', 'thickness : 3000000',
         'elastic : Ruth_vanilla', 'mode : DS', 'Bethe_model : classical', 'diffMFP : no', 'gen_tables : yes',
         'tol_E : 1e-2', 'tol_W : 1e-3', 'maxScatt: 1000', 'Wc : 10',
         'electron_output : outcome, final_E, final_dir, last_pos', 'scatter_output : type, position, energy']))
-    out = str(tmp_path / 'run.parquet')
-    r = subprocess.run([sys.executable, '-m', 'mcdiscrete_b200', '-i', str(inp), '-o', out, '--format', 'parquet',
+    out = str(tmp_path / ('run.parquet' if fmt == 'parquet' else 'run.h5'))
+    r = subprocess.run([sys.executable, '-m', 'mcdiscrete_b200', '-i', str(inp), '-o', out, '--format', fmt,
                         '--batch', '1000'], cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
+    if fmt == 'hdf5':                  # the reference's store layout (keys input / els / scats, doScatter.py:63-67)
+        assert open(out, 'rb').read(8) == b'\x89HDF\r\n\x1a\n'
     from mcdiscrete_b200.store import read_store
     back = read_store(out)
     assert len(back['els']) == 3000
