@@ -133,6 +133,31 @@ def cpu_sample(n_el, nthreads, tables=None):
     return n_el / dt, float(r['n_ev'].sum()) / dt, dt, tables
 
 
+_PY_TABLES = None
+
+
+def _py_job(first_id):
+    """One job of the reference's pool: numTrajPerJob = 4 electrons (doScatter.py:216-220), Python port."""
+    import mcd_oracle as orc
+    els = orc.run_electrons(WORKLOAD, first_id, 4, 1, _PY_TABLES)
+    return sum(len(e.scats) for e in els)
+
+
+def python_pool_sample(tables, cores, jobs_per_core=60):
+    """The Python restatement under multiprocessing.Pool(cores), one job = 4 electrons like the reference's
+    MapScatterer (doScatter.py:22-95): the reference's own parallel structure at the reference's own speed class."""
+    global _PY_TABLES
+    import multiprocessing as mp
+    _PY_TABLES = tables
+    njobs = cores * jobs_per_core
+    with mp.get_context('fork').Pool(cores) as pool:
+        pool.map(_py_job, [7 * 10 ** 9 + 4 * j for j in range(cores)])             # warm-up: imports, page-in
+        t0 = time.time()
+        ev = sum(pool.map(_py_job, [6 * 10 ** 9 + 4 * j for j in range(njobs)], chunksize=1))
+        dt = time.time() - t0
+    return 4 * njobs / dt, ev / dt, dt, 4 * njobs
+
+
 def run_reference(args, rank):
     """`--impl reference`: the reference's CPU implementation of the path on the host cores.  The reference is
     pure Python and /root/reference does not exist on the GPU box, so this is the oracle port: the C restatement
@@ -155,6 +180,13 @@ def run_reference(args, rank):
     t0 = time.time()
     py = orc.run_electrons(WORKLOAD, 5 * 10 ** 9, 24, 1, tables)
     dtp = time.time() - t0
+    try:
+        pel, pev, pdt, pn = python_pool_sample(tables, cores)
+        py_pool = {'value': pel, 'unit': 'electrons/s', 'events_per_s': pev, 'cores': cores,
+                   'note': 'the same Python restatement in a multiprocessing pool of %d workers, 4 electrons per job like '
+                           'the reference (doScatter.py:216-220): %d electrons in %.1f s' % (cores, pn, pdt)}
+    except Exception as ex:          # noqa: BLE001
+        py_pool = {'unavailable': str(ex)}
     sample = ('%d electrons per step of workload C2 (Si 20 keV DS tilt 70 Emin 10 keV), oracle C restatement, %d '
               'threads; tables at tol_E 1e-3 / tol_W 1e-5 (numpy oracle; lookup cost does not depend on table size)'
               % (n_el, cores))
@@ -168,6 +200,7 @@ def run_reference(args, rank):
         'cpu_baseline': {'value': v, 'unit': 'electrons/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'python_port': {'value': 24 / dtp, 'unit': 'electrons/s', 'cores': 1,
                         'note': 'pure-Python restatement with the reference\'s per-event structure, 24 electrons'},
+        'python_port_pool': py_pool,
         'e2e': {'value': v, 'unit': 'electrons/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }))
 
@@ -180,6 +213,8 @@ def main():
     ap.add_argument('--impl', default='ours')
     ap.add_argument('--num-el', type=int, default=NUM_EL)
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-drain', action='store_true', help='skip the output-drain leg (C3 shape, N = 1 only)')
+    ap.add_argument('--drain-el', type=int, default=1_250_000, help='electrons per two batches of the output-drain leg')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
 
@@ -351,6 +386,33 @@ def main():
     eta = float((r.outcome == 1).mean())
     cnt_e2e = r.counters
 
+    # ---- output drain (north_star (3)): BASELINE C3 shape = Cu, full scatter_output (type, position, energy), rows
+    # regrouped on the device into per-column arrays and drained to pinned host memory, pipelined over two contexts.
+    # Reported beside the headline (N = 1 only): rows/s and the D2H GB/s the drain sustains. ---------------------------
+    drain = None
+    if world == 1 and not args.no_drain:
+        ipc = dict(WORKLOAD, material='Cu', scatter_output=['type', 'position', 'energy'], num_el=args.drain_el)
+        ec = Engine(ipc, device=local)
+        genTables(ipc, engine=ec)
+        nb = args.drain_el // 2
+        for _ in ec.run_batches(2 * nb, nb, first_id=10 ** 13, ordered='columns'):      # warm-up: pin the staging buffers
+            pass
+        torch.cuda.synchronize()
+        t0 = time.time()
+        rows = 0
+        for rr in ec.run_batches(4 * nb, nb, first_id=0, ordered='columns'):
+            rows += len(rr.scats)
+            _ = float(rr.scats['energy'][-1]) + int(rr.scats.offsets[-1])
+        dtc3 = time.time() - t0
+        row_bytes = (ec.row_words - 2) * 4 + 1
+        drain = {'workload': 'C3 shape: Cu 20 keV DS tilt 70, scatter_output = type, position, energy; %d electrons in 4 '
+                             'batches, Engine.run_batches(ordered="columns")' % (4 * nb),
+                 'electrons_per_s': 4 * nb / dtc3, 'rows_per_s': rows / dtc3, 'row_bytes_over_pcie': row_bytes,
+                 'd2h_GBps': (rows * row_bytes + 4 * nb * 40) / dtc3 / 1e9,
+                 'note': 'wall clock incl. kernels, device regrouping (scan + columnar scatter) and D2H into pinned host '
+                         'memory; PCIe-bound'}
+        ec.close()
+
     if rank == 0:
         out = {
             'metric': 'electron trajectories/s', 'value': value, 'unit': 'electrons/s', 'n_gpus': world,
@@ -370,6 +432,7 @@ def main():
             'setup': {'tables_s': t_tables, 'table_shapes': {'Moller': [len(tabs['Moller'].Es), len(tabs['Moller'].Ws)],
                                                              'Gryz0': [len(tabs['Gryz'][0].Es), len(tabs['Gryz'][0].Ws)]},
                       'launch': eng.launch_info(), 'sm_mhz_est_from_mufu': mhz.value},
+            'output_drain': drain,
             'physics': {'backscatter_fraction': eta, 'select_exact_frac': cnt['select_exact'] / max(events_per_step, 1),
                         'nan_clamped': cnt['nan_clamped']},
         }

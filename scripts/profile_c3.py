@@ -11,6 +11,6 @@ ip = dict(material='Cu', E0=20000., Emin=10000., mode='DS', s_tilt=70., maxScatt
           scatter_output=['type', 'position', 'energy'], seed=12345)
 eng = Engine(ip, device=0)
 genTables(ip, engine=eng)
-for rep in range(2):
-    r = eng.run(count=n, first_id=rep * n, pinned=True, ordered=True)
-    print(rep, len(r.scats), r.kernel_ms)
+for rep, mode in enumerate((True, True, 'columns', 'columns')):     # row-major regrouping, then the columnar one
+    r = eng.run(count=n, first_id=(rep % 2) * n, pinned=True, ordered=mode)
+    print(rep, mode, len(r.scats), r.kernel_ms)
