@@ -732,6 +732,9 @@ __global__ void __launch_bounds__(256) scatter_cols(const uint32_t* __restrict__
                                                     int row_words, const unsigned long long* __restrict__ offsets,
                                                     unsigned char* __restrict__ cols, unsigned long long col_stride,
                                                     const unsigned int* __restrict__ nchunks_dev) {
+  // rows per column: a run that dropped rows (pool overflow; the caller re-runs it) has event counts beyond the
+  // stored rows -- such targets are skipped instead of written past the columns
+  const unsigned long long max_rows = col_stride >> 2;
   // enqueued right behind the trajectory kernel (no host round trip): the number of used chunks is still on the device
   if (nchunks_dev) nchunks = min(nchunks, *nchunks_dev);
   unsigned char* type_col = cols + (unsigned long long)(row_words - 2) * col_stride;
@@ -744,6 +747,7 @@ __global__ void __launch_bounds__(256) scatter_cols(const uint32_t* __restrict__
         const uint2* src = reinterpret_cast<const uint2*>(cbase) + (size_t)r * rw2;
         const uint2 head = __ldcs(src);
         const unsigned long long d = offsets[head.x] + (unsigned long long)(head.y & 0xffffffu);
+        if (d >= max_rows) continue;
         type_col[d] = (unsigned char)(head.y >> 24);
         for (int w = 1; w < rw2; ++w) {
           const uint2 v = __ldcs(src + w);
@@ -756,6 +760,7 @@ __global__ void __launch_bounds__(256) scatter_cols(const uint32_t* __restrict__
         const uint32_t* src = cbase + (size_t)r * row_words;
         const uint32_t rel = src[0], w1 = src[1];
         const unsigned long long d = offsets[rel] + (unsigned long long)(w1 & 0xffffffu);
+        if (d >= max_rows) continue;
         type_col[d] = (unsigned char)(w1 >> 24);
         for (int w = 2; w < row_words; ++w)
           reinterpret_cast<uint32_t*>(cols + (unsigned long long)(w - 2) * col_stride)[d] = src[w];

@@ -95,6 +95,17 @@ def test_error_behaviour_and_legacy_wrappers():
     assert ei.value.code == -5
     res = eng.run(count=40000, first_id=0)
     assert res.counters['scat_rows_dropped'] == 0 and len(res.scats) == res.counters['events']
+    # the same overflow through the pipelined columnar path, where the regrouping is already enqueued behind the run
+    # when the dropped rows are noticed: clean error, nothing written past the columns, context usable afterwards
+    eng2 = Engine(ip, device=0)
+    genTables(ip, engine=eng2)
+    with pytest.raises(_lib.MCDError) as ei:
+        for _ in eng2.run_batches(80000, 40000, first_id=0, max_scat_rows=1000, ordered='columns'):
+            pass
+    assert ei.value.code == -5
+    eng2.close()
+    tot = sum(len(r.scats) for r in eng.run_batches(40000, 10000, first_id=0, ordered='columns'))
+    assert tot == res.counters['events']
     with pytest.raises(ValueError):
         Engine(dict(ip, scatter_output=['nonsense']), device=0)
     with pytest.raises(NotImplementedError):
