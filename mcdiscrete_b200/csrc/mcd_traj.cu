@@ -486,10 +486,10 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
       float uz = 0.f, ux = 0.f, tot = 0.f;
       EventRow row;
       if (has_row) {
-        const HotRec hr = ds_hot_fetch(P, e.E);                     // loads first, Philox hides their latency
+        const HotRec hr = ds_hot_fetch<1>(P, e.E);                  // loads first, Philox hides their latency
         const float4 u = event_uniforms(P, first_id + rel_id, ev);
         EventMid mid;
-        ds_phase_a<S>(P, e, u, row, mid, tot, hr);
+        ds_phase_a<S, 1>(P, e, u, row, mid, tot, hr);
         outcome = row.outcome;
         slot = row.slot;
         flags = row.flags;
@@ -601,8 +601,9 @@ bool pool_enabled() {      // MCD_NO_POOL=1: the plain kernel for statistics-onl
 
 TrajKernel pick_kernel(const DevParams& P, bool scats) {
   if (scats) return pick_kernel_t<true>(P);
-  // statistics-only DS runs use the park-pool kernel
-  if (P.mode == MCD_MODE_DS && pool_enabled()) return pick_kernel_pool<false>(P);
+  // statistics-only DS runs use the park-pool kernel; it is compiled for the per-cell cross-section records only
+  // (runs whose records could not be built -- channel order not static on [Emin, E0] -- take the plain kernel)
+  if (P.mode == MCD_MODE_DS && P.use_sig_poly && pool_enabled()) return pick_kernel_pool<false>(P);
   return pick_kernel_t<false>(P);
 }
 
@@ -826,7 +827,7 @@ cudaError_t mcd_traj_max_blocks(const DevParams& P, bool scats, int sm_count, Tr
 }
 
 int mcd_traj_uses_queue(const DevParams& P, bool scats) {
-  return (!scats && P.mode == MCD_MODE_DS && pool_enabled()) ? 1 : 0;
+  return (!scats && P.mode == MCD_MODE_DS && P.use_sig_poly && pool_enabled()) ? 1 : 0;
 }
 
 cudaError_t mcd_launch_traj(const DevParams& P, const DevOut& O_in, unsigned long long first_id,
