@@ -529,18 +529,16 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
     }
 
     // ---- energy update (electron.py:44-59), retire (saveOutcomes before the rotation), update_direction ---------
+    // (branch-free: W is 0 for a lane that completes no event in this iteration -- dead, parked or sitting out --
+    // so its energy is unchanged, and the absorption test is masked by `done`)
     const float preE = e.E;
-    if (done) {
-      const float En = preE - W;
-      if (En <= P.Emin) {
-        if (outcome < 0) outcome = MCD_OUT_ABS;
-        else flags |= MCD_EVF_DOUBLE;               // reference records a second 'abs' row (Q4)
-      }
-      e.E = En;
-    }
+    const float En = preE - W;
+    const bool absorbed = done && (En <= P.Emin);
+    const bool dbl = absorbed && (outcome >= 0);    // reference records a second 'abs' row (Q4)
+    outcome = (absorbed && outcome < 0) ? MCD_OUT_ABS : outcome;
+    e.E = En;
     if (outcome >= 0) {
-      retire_lane(P, O, s_hist, s_cnt, want_hist, outcome, (flags & MCD_EVF_DOUBLE) != 0, preE, e, rel_id,
-                  ev + (done ? 1u : 0u));
+      retire_lane(P, O, s_hist, s_cnt, want_hist, outcome, dbl, preE, e, rel_id, ev + (done ? 1u : 0u));
       alive = false;
     }
     if (done) {
