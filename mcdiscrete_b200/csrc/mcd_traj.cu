@@ -367,14 +367,12 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
       const int nneed = __popc(need);
       const int rank = __popc(need & lt);
       const int take = min(nneed, n_ready);
-      if (take > 0) {
-        if (!alive && rank < take) {
-          const uint4* q = reinterpret_cast<const uint4*>(pool + (n_ready - 1 - rank) * kSlotWords);
-          pool_unpack(q[0], q[1], q[2], e, rel_id, ev);
-          alive = true;
-        }
-        wst -= (uint32_t)take;
+      if (!alive && rank < take) {                           // (take = 0: no lane)
+        const uint4* q = reinterpret_cast<const uint4*>(pool + (n_ready - 1 - rank) * kSlotWords);
+        pool_unpack(q[0], q[1], q[2], e, rel_id, ev);
+        alive = true;
       }
+      wst -= (uint32_t)take;
       const int nreq = nneed - take;
       if (nreq > 0 && !exhausted) {
         const unsigned still = __ballot_sync(MCD_FULL_MASK, !alive);
@@ -472,10 +470,14 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
       if (ld) {
         slot = (int)((ev >> 24) & 15u);
         outcome = (int)((ev >> 28) & 7u) - 1;
-        flags = (int)(ev >> 31);                   // MCD_EVF_EXACT = 1
+        flags = 0;                                 // (exact picks of phase A were counted when they happened)
         ev &= 0xffffffu;
         ds_table_event<S>(P, e, __uint_as_float(t.z), __uint_as_float(t.w), __uint_as_float(t.x), slot, flags, W, om);
         done = true;
+        if (flags) {                               // rare: counted here, not after every event of every iteration
+          if (flags & MCD_EVF_NANCLAMP) atomicAdd(&s_cnt[kCntNan], 1u);
+          if (flags & MCD_EVF_EXACT) atomicAdd(&s_cnt[kCntExact], 1u);
+        }
       }
     } else {
       // ---- normal iteration of trajectory_DS: an alive lane executes one event or, past maxScatt, retires as
@@ -489,7 +491,7 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
         const HotRec hr = ds_hot_fetch<1>(P, e.E);                  // loads first, Philox hides their latency
         const float4 u = event_uniforms(P, first_id + rel_id, ev);
         EventMid mid;
-        ds_phase_a<S, 1>(P, e, u, row, mid, tot, hr);
+        ds_phase_a<S, 1>(P, e, u, row, mid, tot, hr, &s_cnt[kCntExact]);
         outcome = row.outcome;
         slot = row.slot;
         flags = row.flags;
@@ -510,7 +512,7 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
         if (park) {
           if (r < room) {
             uint32_t* w = pool + (top - r) * kSlotWords;
-            pool_put(w, e, rel_id, ev | ((uint32_t)slot << 24) | ((uint32_t)(outcome + 1) << 28) | ((uint32_t)(flags & 1) << 31));
+            pool_put(w, e, rel_id, ev | ((uint32_t)slot << 24) | ((uint32_t)(outcome + 1) << 28));
             *reinterpret_cast<uint4*>(w + 12) = make_uint4(__float_as_uint(uz), __float_as_uint(uphi), __float_as_uint(ux), __float_as_uint(tot));
             alive = false;
             outcome = -1;
@@ -522,6 +524,8 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
             slot = __float_as_int(r4.z);
             flags = __float_as_int(r4.w);
             done = true;
+            if (flags & MCD_EVF_NANCLAMP) atomicAdd(&s_cnt[kCntNan], 1u);
+            if (flags & MCD_EVF_EXACT) atomicAdd(&s_cnt[kCntExact], 1u);
           }
         }
         __syncwarp();
@@ -544,10 +548,6 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
     if (done) {
       rotate_dir(e.dx, e.dy, e.dz, e.yx, e.yy, e.yz, 1.0f - om, om, uphi);
       if (want_chan) atomicAdd(&s_cnt[kCntChan + slot_channel(P.m, slot)], 1u);
-      if (flags & (MCD_EVF_NANCLAMP | MCD_EVF_EXACT)) {
-        if (flags & MCD_EVF_NANCLAMP) atomicAdd(&s_cnt[kCntNan], 1u);
-        if (flags & MCD_EVF_EXACT) atomicAdd(&s_cnt[kCntExact], 1u);
-      }
       ++ev;
     }
   }
