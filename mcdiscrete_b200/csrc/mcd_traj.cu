@@ -413,11 +413,14 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
     // at an average of 12 live lanes.  Parked electrons are searched first (forced batch), so the queue only holds
     // plain states. ---------------------------------------------------------------------------------------------
     bool tail = false;
+    // batch trigger: while ids are left all 32 lanes are alive, so it is one masked compare of the packed counters
+    bool batch = (wst & 0xff00u) >= ((uint32_t)kBatchMin << 8);
     if (exhausted) {
       am = __ballot_sync(MCD_FULL_MASK, alive);
       a = __popc(am);
       if (a == 0 && n_pend == 0) break;
       tail = (a + n_pend <= O.dump_T);
+      batch = n_pend > 0 && (n_pend >= min(a, kBatchMin) || tail);
       if (tail && n_pend == 0) {
         const int leader = __ffs(am) - 1;
         unsigned long long base = 0ull;
@@ -437,8 +440,10 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
 
     bool done = false;                             // this lane completes an event in this iteration
     int outcome = -1, slot = 0, flags = 0;
-    float W = 0.f, om = 0.f, uphi = 0.f;
-    if (n_pend > 0 && (n_pend >= min(a, kBatchMin) || tail)) {
+    // W must be 0 for a lane that completes no event (branch-free energy update below); om / uphi are read under
+    // `done` only and are deliberately left without an initialiser (no zeroing instructions per iteration)
+    float W = 0.f, om, uphi;
+    if (batch) {
       // ---- BATCH iteration: current electrons -> ready entries, parked electrons -> lanes, then search ----------
       // (the two pool regions may overlap: all lanes read their parked entry before any lane stores)
       const int nb = min(n_pend, 32);
@@ -485,7 +490,7 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
       const bool has_row = alive && (ev < (uint32_t)P.maxScatt);
       if (alive && !has_row) outcome = MCD_OUT_LONG;
       bool park = false;
-      float uz = 0.f, ux = 0.f, tot = 0.f;
+      float uz, ux, tot;                           // read under `park` only
       EventRow row;
       if (has_row) {
         const HotRec hr = ds_hot_fetch<1>(P, e.E);                  // loads first, Philox hides their latency
