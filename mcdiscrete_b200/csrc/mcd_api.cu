@@ -296,6 +296,9 @@ int build_sig_hot(mcd_ctx* c, const int* order) {
       P.hot_shift = 23 - logM;
       P.hot_base = (uint32_t)(((uint32_t)(e_min + 127) << 23) >> P.hot_shift);
       P.hot_ncell = ncell;
+      P.hot_mask = (1u << P.hot_shift) - 1u;
+      P.hot_last = (uint32_t)(ncell - 1);
+      P.hot_scale = ldexpf(1.0f, -P.hot_shift);
       c->sig_hot_err = worst_lin;
       if (worst_tot > c->sig_poly_err) c->sig_poly_err = worst_tot;
       return 1;

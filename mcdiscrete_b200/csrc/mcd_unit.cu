@@ -57,8 +57,8 @@ __global__ void k_cum(const __grid_constant__ DevParams P, const float* E, uint6
       cum_out[i * nch + k] = fmaf(fmaf(c.z, x, c.y), x, c.x);
     }
     // the hot record: Ruth and Ruth+Quinn boundaries (linear) and the total (quadratic), finer cells
-    const uint32_t hc = min((bits >> P.hot_shift) - P.hot_base, (uint32_t)(P.hot_ncell - 1));
-    const float hx = (float)(bits & ((1u << P.hot_shift) - 1u)) * __uint_as_float((uint32_t)(127 - P.hot_shift) << 23);
+    const uint32_t hc = min((bits >> P.hot_shift) - P.hot_base, P.hot_last);
+    const float hx = (float)(bits & P.hot_mask) * P.hot_scale;
     const float4 h0 = __ldg(P.sig_hot + 2 * (size_t)hc), h1 = __ldg(P.sig_hot + 2 * (size_t)hc + 1);
     cum_out[i * nch + 0] = fmaf(h0.y, hx, h0.x);
     cum_out[i * nch + 1] = fmaf(h0.w, hx, h0.z);
