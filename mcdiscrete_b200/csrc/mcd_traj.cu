@@ -25,6 +25,15 @@ constexpr int kThreads = MCD_THREADS;
 #ifndef MCD_MIN_BLOCKS
 #define MCD_MIN_BLOCKS 6          // 6 x 192 threads = 36 warps per SM at 56 registers (measured best: r1h notes)
 #endif
+// the park-pool kernel has its own geometry: 256 threads x 4 blocks = 32 warps per SM at 64 registers (no spills) and
+// 148 KB of shared memory, which leaves more L1 than 192 x 6 (r2c / r2d A/B runs: -1.8 % on C2)
+#ifndef MCD_POOL_THREADS
+#define MCD_POOL_THREADS 256
+#endif
+#ifndef MCD_POOL_MIN_BLOCKS
+#define MCD_POOL_MIN_BLOCKS 4
+#endif
+constexpr int kPoolThreads = MCD_POOL_THREADS;
 constexpr int kCntOutcome = 0;       // 5
 constexpr int kCntEvents = 5;
 constexpr int kCntDone = 6;
@@ -94,7 +103,7 @@ __device__ __forceinline__ void retire_lane(const DevParams& P, const DevOut& O,
 __device__ __forceinline__ void flush_block_stats(const DevOut& O, const unsigned int* s_hist,
                                                   const unsigned int* s_cnt, const unsigned long long* s_rows,
                                                   bool want_scats, bool want_chan) {
-  for (int i = threadIdx.x; i < MCD_HIST_TOTAL; i += kThreads) {
+  for (int i = threadIdx.x; i < MCD_HIST_TOTAL; i += blockDim.x) {
     const unsigned int v = s_hist[i];
     if (v) atomicAdd(O.stats + i, (unsigned long long)v);
   }
@@ -329,19 +338,19 @@ __device__ __forceinline__ void pool_unpack(const uint4& a, const uint4& b, cons
   OP(0, e.E) OP(1, e.x) OP(2, e.y) OP(3, e.z) OP(4, e.dx) OP(5, e.dy) OP(6, e.dz) OP(7, e.yx) OP(8, e.yy) OP(9, e.yz)
 
 template <int S, bool RESUME>
-__global__ void __launch_bounds__(kThreads, MCD_MIN_BLOCKS)
+__global__ void __launch_bounds__(kPoolThreads, MCD_POOL_MIN_BLOCKS)
 traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsigned long long first_id,
                  const unsigned long long count_arg) {
   // RESUME pass: the "ids" are the entries of the leftover queue the previous pass wrote; only as many blocks as
   // are needed to give every lane two electrons (lanes + pool) do any work
   const unsigned long long count = RESUME ? *O.rq_in_count : count_arg;
-  if (RESUME && (unsigned long long)blockIdx.x * (2ull * kThreads) >= count) return;
+  if (RESUME && (unsigned long long)blockIdx.x * (2ull * kPoolThreads) >= count) return;
   __shared__ unsigned int s_hist[MCD_HIST_TOTAL];
   __shared__ unsigned int s_cnt[kCntTotal];
-  __shared__ __align__(16) uint32_t s_pool[kThreads / 32][kSlotWords * kPoolSlots];
+  __shared__ __align__(16) uint32_t s_pool[kPoolThreads / 32][kSlotWords * kPoolSlots];
 
-  for (int i = threadIdx.x; i < MCD_HIST_TOTAL; i += kThreads) s_hist[i] = 0u;
-  for (int i = threadIdx.x; i < kCntTotal; i += kThreads) s_cnt[i] = 0u;
+  for (int i = threadIdx.x; i < MCD_HIST_TOTAL; i += kPoolThreads) s_hist[i] = 0u;
+  for (int i = threadIdx.x; i < kCntTotal; i += kPoolThreads) s_cnt[i] = 0u;
   __syncthreads();
 
   const unsigned lane = threadIdx.x & 31u;
@@ -804,8 +813,9 @@ unsigned long long mcd_order_tiles(unsigned long long count) {
 cudaError_t mcd_traj_max_blocks(const DevParams& P, bool scats, int sm_count, TrajLaunchInfo* info) {
   TrajKernel k = pick_kernel(P, scats);
   if (!k) return cudaErrorInvalidValue;
+  const int threads = mcd_traj_uses_queue(P, scats) ? kPoolThreads : kThreads;     // (queue <=> park-pool kernel)
   int per_sm = 0;
-  cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kThreads, 0);
+  cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, 0);
   if (err != cudaSuccess) return err;
   cudaFuncAttributes fa;
   err = cudaFuncGetAttributes(&fa, k);
@@ -822,7 +832,7 @@ cudaError_t mcd_traj_max_blocks(const DevParams& P, bool scats, int sm_count, Tr
   if (pct > 100) pct = 100;
   cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
   info->blocks = per_sm * sm_count;
-  info->threads = kThreads;
+  info->threads = threads;
   info->regs = fa.numRegs;
   info->blocks_per_sm = per_sm;
   info->launches = 1;
@@ -864,7 +874,7 @@ cudaError_t mcd_launch_traj(const DevParams& P, const DevOut& O_in, unsigned lon
     O.rq_out_count = last ? nullptr : O_in.rq_counts + p;
     O.dump_T = last ? -1 : dump_T;
     if (p == 0) {
-      k<<<li.blocks, kThreads, 0, stream>>>(P, O, first_id, count);
+      k<<<li.blocks, li.threads, 0, stream>>>(P, O, first_id, count);
     } else {
       TrajKernel kr = pick_kernel_pool<true>(P);
       // same shared-memory carve-out as the first pass
@@ -874,7 +884,7 @@ cudaError_t mcd_launch_traj(const DevParams& P, const DevOut& O_in, unsigned lon
         int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
         cudaFuncSetAttribute(kr, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
       }
-      kr<<<li.blocks, kThreads, 0, stream>>>(P, O, first_id, count);
+      kr<<<li.blocks, li.threads, 0, stream>>>(P, O, first_id, count);
     }
     err = cudaGetLastError();
     if (err != cudaSuccess) return err;
