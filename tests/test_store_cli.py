@@ -85,3 +85,35 @@ def test_store_name_and_cli_options():
     assert (u, f, out, fmt, batch) == (True, 'x.file', None, 'parquet', 1000)
     with pytest.raises(SystemExit):
         dealWithInput(['-h'])
+
+
+def test_columnar_scats_view_equals_row_view(tmp_path):
+    """ScatCols (the host view of mcd_drain_scats_columns: one contiguous array per column, no id / event words)
+    exposes the same columns as ScatRows of the same rows in trajectory order, and the store writes the same file."""
+    from mcdiscrete_b200.engine import ScatCols
+    res, rows = _fake_result()
+    sr = res.sorted_scats()                                  # row-major, trajectory order, with offsets
+    n = len(sr)
+    word_of = sr.word_of
+    stride = ((4 * n + 255) // 256) * 256
+    nf = 4                                                   # x, y, z, energy = row words 2..5
+    block = np.zeros(nf * stride + n, np.uint8)
+    for j in range(nf):
+        block[j * stride:j * stride + 4 * n] = np.ascontiguousarray(sr.words[:, 2 + j]).view(np.uint8)
+    block[nf * stride:] = (sr.words[:, 1] >> 24).astype(np.uint8)
+    sc = ScatCols(block, n, stride, nf * stride, word_of, sr.first_id, sr.offsets)
+    assert sc.keys() == sr.keys() and len(sc) == n
+    for k in sr.keys():
+        assert np.array_equal(sc[k], sr[k]), k
+        assert sc[k].dtype == sr[k].dtype, k
+    assert sc['energy'].flags['C_CONTIGUOUS'] and sc['type'].flags['C_CONTIGUOUS']
+    res_c = RunResult(res.first_id, res.count, res.els, sc, {}, 0.0)
+    assert res_c.sorted_scats() is sc
+    a, b = str(tmp_path / 'rows.h5'), str(tmp_path / 'cols.h5')
+    for path, r in ((a, res), (b, res_c)):
+        with ResultStore(path, IP, fmt='hdf5') as st:
+            st.append_result(r, NAMES)
+    if open(a, 'rb').read(8) == b'\x89HDF\r\n\x1a\n' and not __import__('mcdiscrete_b200.store', fromlist=['x']).have_pytables():
+        assert open(a, 'rb').read() == open(b, 'rb').read()  # the self-contained writer is deterministic
+    ra, rb = read_store(a), read_store(b)
+    assert ra['scats'].equals(rb['scats']) and ra['els'].equals(rb['els'])
