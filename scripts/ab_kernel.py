@@ -16,6 +16,8 @@ WL = {
     'Cu': dict(material='Cu', E0=20000., Emin=10000., mode='DS', s_tilt=70.),
     'Au': dict(material='Au', E0=30000., Emin=15000., mode='DS', s_tilt=0., maxScatt=10000),
     'cont': dict(material='Al', E0=20000., Emin=500., mode='continuous', Bethe_model='classical', s_tilt=70.),
+    'contJL': dict(material='Al', E0=20000., Emin=500., mode='continuous', Bethe_model='JL', s_tilt=70.),
+    'contEx': dict(material='Cu', E0=20000., Emin=500., mode='continuous', Bethe_model='explicit', s_tilt=70.),
 }
 
 
