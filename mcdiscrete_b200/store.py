@@ -197,7 +197,7 @@ class ResultStore:
         self.path = path
         self._pq = {}
         self._h5 = None
-        if fmt == 'hdf5' and not have_pytables():
+        if fmt == 'h5lite' or (fmt == 'hdf5' and not have_pytables()):      # 'h5lite' forces the self-contained writer
             from . import h5lite
             if os.path.exists(path):
                 os.remove(path)
@@ -226,7 +226,7 @@ class ResultStore:
                     os.remove(os.path.join(path, f))
             json.dump({k: str(v) for k, v in self.inputPar.items()}, open(os.path.join(path, 'input.json'), 'w'), indent=1)
         else:
-            raise ValueError('fmt must be auto, hdf5 or parquet')
+            raise ValueError('fmt must be auto, hdf5, h5lite or parquet')
 
     def append(self, key, df):
         if len(df) == 0:
@@ -288,7 +288,7 @@ class ResultStore:
         return False
 
 
-def read_store(path):
+def read_store(path, reader='auto'):
     """Read back {'input': Series/dict, 'els': DataFrame, 'scats': DataFrame or None} from either back end."""
     import pandas as pd
     if os.path.isdir(path):
@@ -297,7 +297,7 @@ def read_store(path):
             f = os.path.join(path, key + '.parquet')
             out[key] = pd.read_parquet(f) if os.path.exists(f) else None
         return out
-    if not have_pytables():
+    if reader == 'h5lite' or not have_pytables():
         return read_store_h5lite(path)
     with pd.HDFStore(path, mode='r') as st:
         return {'input': st['input'], 'els': st['els'], 'scats': st['scats'] if '/scats' in st.keys() else None}

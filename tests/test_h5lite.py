@@ -218,3 +218,26 @@ def test_store_writes_the_pandas_frame_table_contract(tmp_path):
     assert back['els']['final_E'].dtype == np.float64 and len(back['scats']) == 2 * len(rows)
     assert list(back['scats']['type'][:3]) == ['Ruth', 'Moller', 'Gryz1s']
     assert list(back['scats']['x']) == 2 * [float(r[2]) for r in rows]
+
+
+def test_h5lite_file_opens_with_pandas_where_pytables_exists(tmp_path):
+    """The compatibility check this image cannot run (no PyTables / libhdf5 here): wherever `tables` is installed, a
+    store written by the self-contained writer must open with pandas.read_hdf exactly like one written by pandas."""
+    pytest.importorskip('tables')
+    import pandas as pd
+    from test_store_cli import _fake_result, IP, NAMES
+    from mcdiscrete_b200.store import ResultStore, read_store
+    res, rows = _fake_result()
+    path = str(tmp_path / 'lite.h5')
+    with ResultStore(path, IP, fmt='h5lite', chunk_rows=4) as st:
+        st.append_result(res, NAMES)
+        st.append_result(res, NAMES)
+    mine = read_store(path, reader='h5lite')
+    for key in ('els', 'scats'):
+        df = pd.read_hdf(path, key)
+        assert list(df.columns) == list(mine[key].columns) and len(df) == len(mine[key])
+        for c in df.columns:
+            assert list(df[c]) == list(mine[key][c]), (key, c)
+    assert pd.read_hdf(path, 'input').iloc[0]['material'] == 'Si'
+    sel = pd.read_hdf(path, 'scats', where='type == "Ruth"')          # data columns are queryable
+    assert len(sel) == int((mine['scats']['type'] == 'Ruth').sum())
