@@ -365,7 +365,7 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
 #define n_pend ((int)((wst >> 8) & 0xffu))
 #define exhausted ((wst >> 16) != 0u)
 
-  bool alive = false;
+  int alive = 0;                     // (int, not bool: the compiler keeps bools of this loop packed in bytes)
   ElState e;
   uint32_t rel_id = 0u, ev = 0u;
 
@@ -447,7 +447,7 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
       }
     }
 
-    bool done = false;                             // this lane completes an event in this iteration
+    int done = 0;                                  // this lane completes an event in this iteration
     int outcome = -1, slot = 0, flags = 0;
     // W must be 0 for a lane that completes no event (branch-free energy update below); om / uphi are read under
     // `done` only and are deliberately left without an initialiser (no zeroing instructions per iteration)
