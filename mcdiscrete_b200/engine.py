@@ -327,6 +327,7 @@ class Engine:
 
     def launch(self, first_id, count, stream=None):
         """Asynchronous mcd_run on `stream` (a raw cudaStream_t integer; None = default stream)."""
+        self._order_enqueued = False               # mcd_run invalidates any regrouping of the previous run
         self._ck(self.lib.mcd_run(self.ctx, int(first_id), int(count), C.c_void_p(stream or 0)))
 
     def sync(self, stream=None):
