@@ -200,3 +200,19 @@ def test_edge_cases_empty_and_degenerate_runs():
     b = eng.run(count=3, first_id=2 ** 45 + 12344)
     assert a.els[0] == b.els[1]
     eng.close()
+
+
+def test_top_level_run():
+    """mcdiscrete_b200.run(inputPar): parameters -> columnar results in one call."""
+    import numpy as np
+    import mcdiscrete_b200 as mcd
+    ip = dict(num_el=2000, E0=20000., Emin=15000., material='Si', s_tilt=70., thickness=3e6, elastic='Ruth_vanilla',
+              mode='DS', Bethe_model='classical', diffMFP=False, gen_tables=True, tol_E=1e-2, tol_W=1e-3,
+              maxScatt=1000, Wc=10., electron_output=['outcome', 'final_E'], scatter_output=['type', 'energy'])
+    a = mcd.run(ip, seed=7, device=0)
+    b = mcd.run(ip, seed=7, device=0, ordered=True)
+    assert a.count == 2000 and len(a.els) == 2000 and a.counters['electrons_done'] == 2000
+    assert a.scats.offsets[-1] == len(a.scats) == a.counters['events']
+    assert np.array_equal(a.els, b.els) and np.array_equal(a.scats['energy'], b.scats['energy'])
+    c = mcd.run(dict(ip, mode='cont', Emin=2000.), seed=7, device=0, count=500)
+    assert c.count == 500 and set(np.unique(c.outcome)) <= {0, 1, 2, 4}
