@@ -674,6 +674,8 @@ class Writer:
             entries, level = nxt, level + 1
 
     def _table_header(self, t):
+        if t.n_pending and not t.chunks:
+            t.chunk_rows = t.n_pending                                 # a table smaller than one chunk: exact fit
         if t.n_pending:                                                # last, partial chunk: stored at full size
             buf = np.zeros(t.chunk_rows, t.dtype)
             buf[:t.n_pending] = np.concatenate(t.pending)
@@ -750,3 +752,34 @@ class Writer:
     def __exit__(self, *a):
         self.close()
         return False
+
+
+def describe(path, out=None):
+    """Print the tree of an HDF5 file this module can read (groups, datasets with shape / dtype / layout, number of
+    attributes): `python -m mcdiscrete_b200.h5lite run.h5`."""
+    import sys
+    out = out or sys.stdout
+    with File(path) as f:
+        out.write('%s: superblock v%d, base address %d, end of file %d\n' % (path, f.superblock_version, f.base, f.eof))
+
+        def walk(node, depth):
+            for name in node.keys():
+                ch = node[name]
+                pad = '  ' * depth
+                if ch.is_group:
+                    out.write('%s%s/  (%d attributes)\n' % (pad, name, len(ch.attrs)))
+                    walk(ch, depth + 1)
+                else:
+                    lay = ch.layout
+                    extra = ', chunks of %s' % (lay['chunk'],) if lay['class'] == 'chunked' else ''
+                    dt = ch.dtype
+                    fields = ', '.join('%s:%s' % (n, dt.fields[n][0].str) for n in dt.names) if dt is not None and dt.names else str(dt)
+                    out.write('%s%s  shape %s, %s%s, [%s]  (%d attributes)\n' % (pad, name, ch.shape, lay['class'], extra,
+                                                                               fields, len(ch.attrs)))
+        walk(f, 1)
+
+
+if __name__ == '__main__':
+    import sys
+    for p in sys.argv[1:]:
+        describe(p)

@@ -189,7 +189,7 @@ class _H5LiteTable:
 class ResultStore:
     """Appendable store; use as a context manager."""
 
-    def __init__(self, path, inputPar, fmt='auto', chunk_rows=1 << 18):
+    def __init__(self, path, inputPar, fmt='auto', chunk_rows=1 << 16):
         self.inputPar = dict(inputPar)
         if fmt == 'auto':
             fmt = 'hdf5'

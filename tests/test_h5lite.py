@@ -241,3 +241,21 @@ def test_h5lite_file_opens_with_pandas_where_pytables_exists(tmp_path):
     assert pd.read_hdf(path, 'input').iloc[0]['material'] == 'Si'
     sel = pd.read_hdf(path, 'scats', where='type == "Ruth"')          # data columns are queryable
     assert len(sel) == int((mine['scats']['type'] == 'Ruth').sum())
+
+
+def test_small_tables_fit_exactly_and_describe(tmp_path):
+    """A table smaller than one chunk is stored with a chunk of exactly its size (no 5 MB file for 5 rows), and
+    `python -m mcdiscrete_b200.h5lite file` prints the tree."""
+    import io
+    dt = np.dtype([('index', '<i8'), ('v', '<f8')])
+    path = str(tmp_path / 's.h5')
+    with h5lite.Writer(path) as w:
+        t = w.create_table('/els/table', dt, chunk_rows=1 << 16)
+        w.append(t, np.array([(0, 1.0), (1, 2.0), (2, 3.0)], dt))
+    assert os.path.getsize(path) < 4096
+    f = h5lite.File(path)
+    assert f['els/table'].layout['chunk'] == (3,) and list(f['els/table'].read()['v']) == [1.0, 2.0, 3.0]
+    _validate(path)
+    buf = io.StringIO()
+    h5lite.describe(path, buf)
+    assert 'els/' in buf.getvalue() and 'shape (3,), chunked' in buf.getvalue()
