@@ -259,3 +259,47 @@ def test_small_tables_fit_exactly_and_describe(tmp_path):
     buf = io.StringIO()
     h5lite.describe(path, buf)
     assert 'els/' in buf.getvalue() and 'shape (3,), chunked' in buf.getvalue()
+
+
+def test_roundtrip_property_random_tables(tmp_path):
+    """Property test (hypothesis): any mix of int / float / fixed-string columns, any row count and chunk size, any
+    split into appends -> the file validates and reads back bit for bit."""
+    hyp = pytest.importorskip('hypothesis')
+    from hypothesis import given, settings, strategies as st_
+
+    kinds = st_.sampled_from(['<i8', '<i4', '<u2', '<f8', '<f4', 'S1', 'S7', 'S16'])
+    counter = [0]
+
+    @settings(max_examples=40, deadline=None)
+    @given(cols=st_.lists(kinds, min_size=1, max_size=6), rows=st_.integers(0, 700), chunk=st_.integers(1, 97),
+           parts=st_.integers(1, 9), seed=st_.integers(0, 2 ** 31))
+    def check(cols, rows, chunk, parts, seed):
+        rng = np.random.default_rng(seed)
+        dt = np.dtype([('index', '<i8')] + [('c%d' % i, k) for i, k in enumerate(cols)])
+        data = np.zeros(rows, dt)
+        data['index'] = np.arange(rows)
+        for i, k in enumerate(cols):
+            sub = np.dtype(k)
+            if sub.kind == 'S':
+                raw = rng.integers(97, 123, (rows, sub.itemsize), dtype=np.uint8)
+                raw[rng.random((rows, sub.itemsize)) < 0.2] = 0          # embedded / trailing NULs
+                data['c%d' % i] = np.frombuffer(raw.tobytes(), dtype=sub, count=rows) if rows else np.zeros(0, sub)
+            elif sub.kind == 'f':
+                data['c%d' % i] = rng.normal(size=rows).astype(sub)
+            else:
+                info = np.iinfo(sub)
+                data['c%d' % i] = rng.integers(info.min, info.max, rows, dtype=sub, endpoint=True)
+        counter[0] += 1
+        path = str(tmp_path / ('p%d.h5' % counter[0]))
+        with h5lite.Writer(path) as w:
+            t = w.create_table('/g/table', dt, chunk_rows=chunk)
+            for part in np.array_split(data, parts):
+                w.append(t, part)
+            w.set_attrs('/g/table', {'NROWS': np.int64(rows)})
+        _validate(path)
+        back = h5lite.File(path)['g/table']
+        assert back.dtype == dt and back.shape == (rows,)
+        assert back.read().tobytes() == data.tobytes()
+        os.remove(path)
+
+    check()
