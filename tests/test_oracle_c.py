@@ -75,6 +75,27 @@ def test_c_port_matches_python_port_elastic_models(elastic):
     np.testing.assert_allclose(c['final_E'], [e.els[0][1] for e in py], rtol=1e-12)
 
 
+def test_c_port_thin_film_and_Au_goldens():
+    """The C port against the reference's own rows for the thin film ('trsm') and Au (8 shells) cases."""
+    g = np.load(os.path.join(GOLD, 'traj_DS_Si_thin.npz'))
+    ip = dict(E0=20000., Emin=15000., material='Si', s_tilt=0., thickness=9000., mode='DS', maxScatt=1000, Wc=10.)
+    c = oc.run(ip, int(g['ids'][0]), len(g['ids']), 12345, _golden_tabs('Si_15k_small'))
+    assert np.array_equal(c['outcome'], g['outcome']) and np.array_equal(c['n_ev'], g['n_ev'])
+    np.testing.assert_allclose(c['final_E'], g['final_E'], rtol=1e-12)
+    np.testing.assert_allclose(c['last_pos'], g['last_pos'], rtol=1e-10, atol=1e-8)
+    g = np.load(os.path.join(GOLD, 'traj_DS_Au.npz'))
+    T = {}
+    for nm, kind in (('moller', 'Moller'), ('gryz0', 'Gryz')):
+        t = o.ProbTable.__new__(o.ProbTable)
+        t.Ws, t.Es, t.table = g[nm + '_Ws'], g[nm + '_Es'], g[nm + '_table']
+        T[kind] = t if kind == 'Moller' else [t]
+    ip = dict(E0=30000., Emin=27000., material='Au', s_tilt=0., thickness=3e6, mode='DS', maxScatt=1000, Wc=10.)
+    c = oc.run(ip, 0, 3, 12345, T, event_rows=int(g['n_ev'].sum()))
+    assert np.array_equal(c['outcome'], g['outcome']) and np.array_equal(c['n_ev'], g['n_ev'])
+    assert np.array_equal(c['events'][:, 0].astype(int), g['type'])
+    np.testing.assert_allclose(c['events'][:, 7], g['energy'], rtol=1e-12)
+
+
 def test_c_port_threads_and_q4():
     g = np.load(os.path.join(GOLD, 'traj_DS_Si_q4.npz'))
     T = {}

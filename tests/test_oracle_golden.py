@@ -206,6 +206,23 @@ def test_trajectories_cont_elastic_models(elastic):
     assert els[0].scats[0]['type'] == elastic          # scattering.py:834
 
 
+def test_trajectories_DS_thin_film_and_Au():
+    """oracle/gen_golden_more.py: 'trsm' outcomes on a 9000 A film (electron.py:73-81) and Au with its 8 core shells."""
+    g = load('traj_DS_Si_thin.npz')
+    ip = dict(E0=20000., Emin=15000., material='Si', s_tilt=0., thickness=9000., mode='DS', maxScatt=1000, Wc=10.)
+    mat = o.Material('Si')
+    els = o.run_electrons(ip, int(g['ids'][0]), len(g['ids']), 12345, _tables_from_golden('Si_15k_small', mat), mat)
+    cols = ['type', 'position', 'pathl', 'E', 'E_loss', 'pol_angle', 'az_angle', 'energy', 'direction']
+    _check_traj(g, els, cols)
+    assert (g['outcome'] == 2).sum() > 10 and (g['outcome'] == 0).sum() > 0        # transmitted and absorbed
+    g = load('traj_DS_Au.npz')
+    ip = dict(E0=30000., Emin=27000., material='Au', s_tilt=0., thickness=3e6, mode='DS', maxScatt=1000, Wc=10.)
+    mat = o.Material('Au')
+    els = o.run_electrons(ip, 0, 3, 12345, _tables_from_golden('traj_DS_Au.npz', mat), mat)
+    _check_traj(g, els, cols)
+    assert len(np.unique(g['type'])) >= 8                                           # most of the 11 channels occur
+
+
 def test_philox_known_answer():
     """Random123 known-answer vectors for Philox4x32-10."""
     assert o.philox4x32_10((0, 0, 0, 0), (0, 0)) == (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)
