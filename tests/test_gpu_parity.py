@@ -386,6 +386,8 @@ def _golden_traj_check(eng, g, ids, atol_pos=0.5):
     ('traj_DS_Si.npz', 'Si_15k_small', {}),
     ('traj_DS_Cu.npz', 'Cu_10k_small', dict(material='Cu', Emin=10000.)),
     ('traj_DS_Si_long.npz', 'Si_15k_small', dict(maxScatt=5)),
+    ('traj_DS_Si_thin.npz', 'Si_15k_small', dict(thickness=9000., s_tilt=0.)),                 # 'trsm' outcomes
+    ('traj_DS_Au.npz', 'traj_DS_Au.npz', dict(material='Au', E0=30000., Emin=27000., s_tilt=0.)),   # 8 core shells
 ])
 def test_full_trajectories_vs_reference_golden(fname, key, kw):
     """Whole trajectories on the reference's own tables and the same Philox uniforms: the GPU follows the
