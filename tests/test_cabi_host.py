@@ -84,6 +84,21 @@ def test_readInput_and_column_contract():
                                                          'last_x', 'last_y', 'last_z']
 
 
+def test_readInput_matches_the_reference_parser():
+    """tests/golden/readInput.json = what the reference's own readInput (fileTools.py:8-46) returns for the files
+    under tests/data/ (oracle/gen_golden_input.py): inline comments without a blank, extra float keys, yes/no flags,
+    and its quirk of stripping blanks but not tabs (' \tCu' stays '\tCu')."""
+    from mcdiscrete_b200.fileTools import readInput
+    gold = json.load(open(os.path.join(GOLD, 'readInput.json')))
+    assert set(gold) == {'input.file', 'input_variants.file'}
+    for name, want in gold.items():
+        got = readInput(os.path.join(ROOT, 'tests', 'data', name))
+        assert got == want and list(got) == list(want), name          # same values, same key order
+        for k in want:
+            assert type(got[k]) is type(want[k]), (name, k)
+    assert gold['input_variants.file']['material'] == '\tCu'
+
+
 def test_material_matches_reference():
     from mcdiscrete_b200.material import material
     F = json.load(open(os.path.join(GOLD, 'formulas.json')))
