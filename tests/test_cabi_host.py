@@ -4,6 +4,7 @@ declares, fails loudly without a GPU, and the host-side mirror of the reference 
 import ctypes as C
 import json
 import os
+import sys
 import re
 
 import numpy as np
@@ -97,6 +98,28 @@ def test_readInput_matches_the_reference_parser():
         for k in want:
             assert type(got[k]) is type(want[k]), (name, k)
     assert gold['input_variants.file']['material'] == '\tCu'
+
+
+def test_thingsToSave_zipDict_and_column_order_match_the_reference():
+    """tests/golden/columns.json = the reference's own thingsToSave / zipDict (fileTools.py:67-99, 193-242) and the
+    column order of the DataFrame its listener stores (doScatter.py:112-117), for nine output selections driven
+    through the same scripted addToList calls (oracle/gen_golden_columns.py)."""
+    import copy
+    from mcdiscrete_b200.fileTools import thingsToSave, zipDict, flat_columns
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import gen_golden_columns as gen              # only its call script (no reference import at test time)
+    gold = json.load(open(os.path.join(GOLD, 'columns.json')))
+    assert len(gold) == 9
+    for key, c in gold.items():
+        names = c['requested']
+        dicts = gen.script(thingsToSave, names)
+        assert dicts == c['per_electron'], key
+        merged = {}
+        for d in copy.deepcopy(dicts):
+            merged = zipDict(merged, d)
+        assert merged == c['zipped'] and list(merged) == list(c['zipped']), key
+        which = 'els' if set(names) & {'outcome', 'final_E', 'final_dir', 'last_pos'} else 'scats'
+        assert flat_columns(names, which) == c['frame_columns'], key
 
 
 def test_material_matches_reference():
