@@ -151,3 +151,26 @@ def test_host_axis_search_matches_reference(key):
         g = np.load(os.path.join(GOLD, 'tables_%s.npz' % key))
         assert np.array_equal(T.Ws, g['moller_Ws']) and np.array_equal(T.Es, g['moller_Es'])
         assert np.array_equal(G.Ws, g['gryz0_Ws']) and np.array_equal(G.Es, g['gryz0_Es'])
+
+
+@pytest.mark.parametrize('key', ['C2_Si', 'C3_Cu', 'C4_Au'])
+def test_host_axis_search_default_tolerance(key):
+    """The host axis search at BASELINE's default tolerances (tol_E 1e-4, tol_W 1e-7) against the reference's grids
+    (SHA-1 of the float32 axes, oracle/gen_golden_defaults.py)."""
+    import hashlib
+    from mcdiscrete_b200.material import material
+    from mcdiscrete_b200.probTables import probTable
+    ax = json.load(open(os.path.join(GOLD, 'table_axes_default.json')))[key]
+    ip = ax['input']
+    mat = material(ip['material'])
+    sha = lambda a: hashlib.sha1(np.ascontiguousarray(a, np.float32).tobytes()).hexdigest()
+    for nm, T in (('moller', probTable('Moller', mat.params['name_val'], (ip['Emin'], ip['E0']), ip['tol_E'], ip['tol_W'],
+                                       mat, Wc=ip['Wc'])),
+                  ('gryz0', probTable('Gryzinski', mat.params['name_s'][-1], (ip['Emin'], ip['E0']), ip['tol_E'],
+                                      ip['tol_W'], mat))):
+        T.set_Ws(); T.set_Es()
+        a = ax[nm]
+        assert [T.shell, len(T.Es), len(T.Ws)] == [a['shell'], a['nE'], a['nW']]
+        assert T.Es.dtype == np.float32 and T.Ws.dtype == np.float32
+        assert sha(T.Es) == a['Es_sha1'] and sha(T.Ws) == a['Ws_sha1']
+        assert not T.exhausted

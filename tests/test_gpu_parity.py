@@ -157,7 +157,13 @@ def test_angles_and_rotation():
     assert np.array_equal(np.isnan(c2b)[~edge], np.isnan(ref)[~edge])
     ok = ~np.isnan(ref) & ~np.isnan(c2b)
     assert relerr(c2b[ok], ref[ok]).max() < REL
-    assert relerr(omb[ok], 1 - ref[ok], floor=1e-12).max() < 2e-6 or True
+    # om = 1 - c2 = sin^2(theta/2) is carried separately so that it keeps full RELATIVE precision where c2 -> 1 (the
+    # float64 reference loses it there: 1 - c2 cancels); the exact value is w / (2 (1 + sqrt(1 - w))), w = W/E
+    w64 = W.astype(np.float64) / E2.astype(np.float64)
+    om_exact = w64 / (2.0 * (1.0 + np.sqrt(1.0 - w64)))
+    assert relerr(omb[ok], om_exact[ok], floor=1e-300).max() < REL
+    big = ok & (1 - ref > 1e-6)                                 # where the reference's own 1 - c2 is still accurate
+    assert relerr(omb[big], 1 - ref[big]).max() < 2e-6
     # rotation against the reference's quaternion arithmetic (golden, from electron.update_direction)
     hp = g['hp_in']
     uphi = (hp / math.pi).astype(np.float32)
@@ -216,6 +222,70 @@ def test_tables_mid_tolerance_rows(key):
         assert neq.mean() < 1e-3
         assert np.abs(dev - ref).max() <= np.spacing(np.float32(1.0))
     eng.close()
+
+
+@pytest.mark.parametrize('key', ['C2_Si', 'C3_Cu', 'C4_Au'])
+def test_tables_default_tolerance_rows_and_lookup(key):
+    """BASELINE's DEFAULT tolerances (tol_E 1e-4, tol_W 1e-7; inputFile/input.file:24-25) -- the 0.4-0.6 GB tables the
+    headline numbers run on.  Axes identical to the reference's (SHA-1), eight device-built rows per table within one
+    float32 ulp of the reference's computeBlock rows (oracle/gen_golden_defaults.py), and pickTable bit-exact:
+    (a) on the reference's own rows (spliced into the device table) against the reference's own lookups, (b) on the
+    complete device-built table against the oracle's bisect over the downloaded rows."""
+    import hashlib
+    from mcdiscrete_b200.probTables import genTables
+    ax = json.load(open(os.path.join(GOLD, 'table_axes_default.json')))[key]
+    g = np.load(os.path.join(GOLD, 'tablerows_%s_default.npz' % key))
+    ipk = dict(ax['input'], maxScatt=1000, scatter_output=[])
+    eng = make_engine(**ipk)
+    tabs = genTables(dict(base_input(), **ipk), engine=eng)
+    sha = lambda a: hashlib.sha1(np.ascontiguousarray(a, np.float32).tobytes()).hexdigest()
+    rng = np.random.default_rng(11)
+    for slot, nm, T in ((0, 'moller', tabs['Moller']), (1, 'gryz0', tabs['Gryz'][0])):
+        a = ax[nm]
+        assert [T.shell, len(T.Es), len(T.Ws)] == [a['shell'], a['nE'], a['nW']]
+        assert sha(T.Es) == a['Es_sha1'] and sha(T.Ws) == a['Ws_sha1']
+        full = eng.table_download(slot)
+        idx = g[nm + '_rows_idx']
+        dev, ref = full[idx], g[nm + '_rows']
+        assert np.array_equal(dev == 0, ref == 0)                       # same masked tail
+        neq = dev != ref
+        assert neq.mean() < 1e-3, '%s: %.4f%% entries differ' % (nm, 100 * neq.mean())
+        assert np.abs(dev - ref).max() <= np.spacing(np.float32(1.0))   # float32 rounding ties of the float64 scan only
+        # (b) complete device table: lookups == bisect over the downloaded rows (incl. grid points and their neighbours)
+        OT = o.ProbTable.__new__(o.ProbTable)
+        OT.Ws, OT.Es, OT.table = T.Ws, T.Es, full
+        OT.masked = _LazyMask(full)
+        E = np.concatenate([rng.uniform(T.Es[0] * 1.00001, T.Es[-1], 6000), T.Es[1::97], np.nextafter(T.Es[1::97], np.float32(0)),
+                            np.nextafter(T.Es[:-1:97], np.float32(1e9))]).astype(np.float32)
+        u = rng.random(len(E)).astype(np.float32)
+        u[::7] = u[::7] ** 8                                            # the steep start of the CDF
+        u[3::7] = 1 - (1 - u[3::7]) ** 6                                # the long tail (widest guide buckets)
+        u = np.clip(u, np.float32(2 ** -24), np.float32(1 - 2 ** -24))
+        W, iE, jW = eng.test_lookup(slot, E, u)
+        want = [o.pick_table(OT, float(e), float(v)) for e, v in zip(E, u)]
+        assert np.array_equal(iE, [r[1] for r in want])
+        assert np.array_equal(jW, [r[2] for r in want])
+        assert np.array_equal(W, np.array([r[0] for r in want], np.float32))
+        # (a) the reference's rows spliced in: the reference's own lookups on them, bit for bit
+        full[idx] = ref
+        eng.table_upload(slot, T.Es, T.Ws, full)
+        qE, qu = g[nm + '_lookup_E'], g[nm + '_lookup_u']
+        assert np.array_equal(qE.astype(np.float32), qE) and np.array_equal(qu.astype(np.float32), qu)
+        W, iE, jW = eng.test_lookup(slot, qE, qu)
+        assert set(iE.tolist()) <= set(idx.tolist())
+        assert np.array_equal(W.astype(np.float64), g[nm + '_lookup_W'])
+        del full
+    eng.close()
+
+
+class _LazyMask:
+    """masked[iE] of a table too big to duplicate as a boolean array"""
+
+    def __init__(self, table):
+        self.t = table
+
+    def __getitem__(self, i):
+        return self.t[i] == 0
 
 
 @pytest.mark.parametrize('key', ['Si_15k_small', 'Al_500_small', 'Cu_10k_small'])
@@ -351,13 +421,15 @@ def test_cont_step_injected_uniforms(model):
     eng.close()
 
 
-def _golden_traj_check(eng, g, ids, atol_pos=0.5):
+def _golden_traj_check(eng, g, ids, atol_pos=0.5, min_same=None):
     res = eng.run(count=len(ids), first_id=int(ids[0]))
     sc = res.sorted_scats()
     nev = np.bincount((sc['el'] - int(ids[0])).astype(np.int64), minlength=len(ids))
     gold_first = np.concatenate([[0], np.cumsum(g['n_els'])])[:-1]
     same = (nev == g['n_ev']) & (res.outcome == g['outcome'][gold_first])
-    assert same.mean() >= 0.7, 'only %d/%d trajectories follow the reference event for event' % (same.sum(), len(ids))
+    print('golden trajectories: %d/%d follow the reference event for event' % (same.sum(), len(ids)))
+    assert same.sum() >= (len(ids) if min_same is None else min_same), \
+        'only %d/%d trajectories follow the reference event for event' % (same.sum(), len(ids))
     goff = np.concatenate([[0], np.cumsum(g['n_ev'])])
     off = np.concatenate([[0], np.cumsum(nev)])
     for i in np.flatnonzero(same):

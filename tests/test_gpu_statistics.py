@@ -63,7 +63,10 @@ def _compare(res, ref, n_gpu, n_ref, second_sample=None):
     bad = {k: p for k, p in ps.items() if p <= P_MIN}
     if bad and second_sample is not None:
         ps2 = _ks_table(res, second_sample())
+        print('KS re-test: first sample p = %s, second independent sample p = %s'
+              % ({k: '%.4g' % p for k, p in bad.items()}, {k: '%.4g' % ps2[k] for k in bad}))
         bad = {k: (p, ps2[k]) for k, p in bad.items() if ps2[k] <= P_MIN}
+    print('eta gpu %.4f oracle %.4f; KS p-values %s' % (eta_g, eta_r, {k: '%.3g' % p for k, p in ps.items()}))
     assert not bad, 'KS failures: %s (all: %s)' % (bad, ps)
     return eta_g, eta_r, ps
 
@@ -94,6 +97,81 @@ def test_full_run_statistics_DS(name, E0, Emin, tilt):
     assert h['energy'][0].sum() == bks.sum() == h['polar_deg'][0].sum() == h['depth'][0].sum()
     hist_E, _ = np.histogram(res.els['final_E'][bks], bins=h['energy'][1])
     assert np.abs(hist_E - h['energy'][0]).sum() <= 2e-3 * bks.sum()          # bin-edge rounding only
+    eng.close()
+
+
+# ---- BASELINE's own configurations at the DEFAULT table tolerances (tol_E 1e-4, tol_W 1e-7) ---------------------------
+_DEFAULT_TABLES = {}
+
+
+def _oracle_tables_default(ip):
+    """The numpy oracle's own tables at default tolerances (0.4-0.6 GB each, ~30 s per material), built once per
+    session.  The GPU engine builds ITS tables on the device (the product path): the two sides share nothing."""
+    key = (ip['material'], ip['E0'], ip['Emin'])
+    if key not in _DEFAULT_TABLES:
+        _DEFAULT_TABLES.clear()                       # one material at a time: a set is ~1 GB of host memory
+        _DEFAULT_TABLES[key] = o.gen_tables(ip, strict=False)
+    return _DEFAULT_TABLES[key]
+
+
+@pytest.mark.parametrize('tag,name,E0,Emin,tilt,maxScatt', [
+    ('C2', 'Si', 20000., 10000., 70., 1000), ('C3', 'Cu', 20000., 10000., 70., 1000), ('C4', 'Au', 30000., 15000., 0., 10000)])
+def test_baseline_configs_at_default_tolerances(tag, name, E0, Emin, tilt, maxScatt):
+    """C2 / C3 / C4 of BASELINE.json as they are benchmarked: default-tolerance tables BUILT ON THE DEVICE, 2e5 GPU
+    electrons against 4e4 electrons of the float64 C oracle on the oracle's own default-tolerance tables.  eta within
+    3 sigma, two-sample KS p > 0.01 (energy, exit angles, depth), mean trajectory length within 1 %, and on the same
+    Philox streams > 99.9 % identical outcomes."""
+    from mcdiscrete_b200.probTables import genTables
+    ip = dict(E0=E0, Emin=Emin, material=name, s_tilt=tilt, thickness=3e6, mode='DS', maxScatt=maxScatt, Wc=10.,
+              tol_E=1e-4, tol_W=1e-7, electron_output=['outcome', 'final_E', 'final_dir', 'last_pos'],
+              scatter_output=[], seed=777, elastic='Ruth_vanilla')
+    tabs = _oracle_tables_default(ip)
+    eng = _engine(ip)
+    dtabs = genTables(ip, engine=eng)
+    assert np.array_equal(dtabs['Moller'].Ws, tabs['Moller'].Ws) and np.array_equal(dtabs['Gryz'][0].Es, tabs['Gryz'][0].Es)
+    assert dtabs['Moller'].Es.size * (dtabs['Moller'].Ws.size - 1) >= 99_000_000        # the full-size tables
+    n_gpu, n_ref = 200000, 40000
+    nt = os.cpu_count() or 1
+    res = eng.run(count=n_gpu, first_id=0)
+    assert eng.launch_info()['launches_per_run'] > 1               # the statistics-only (park-pool) kernel of the headline
+    ref = oc.run(ip, 0, n_ref, 4242, tabs, nthreads=nt)
+    _compare(res, ref, n_gpu, n_ref, lambda: oc.run(ip, 0, n_ref, 2024, tabs, nthreads=nt))
+    ev_g = res.counters['events'] / n_gpu
+    assert abs(ev_g - ref['n_ev'].mean()) < 0.01 * ref['n_ev'].mean()
+    same = oc.run(ip, 0, 20000, 777, tabs, nthreads=nt)
+    agree = (res.outcome[:20000] == same['outcome']).mean()
+    print('%s: %.1f events per electron, same-seed outcome agreement %.5f' % (tag, ev_g, agree))
+    assert agree > 0.999, agree
+    eng.close()
+
+
+@pytest.mark.parametrize('name,E0,mode,model', [
+    ('Al', 5000., 'cont', 'JL'), ('Cu', 5000., 'cont', 'explicit'), ('Si', 5000., 'DS', 'classical'),
+    ('Au', 30000., 'cont', 'JL'), ('Si', 30000., 'cont', 'explicit'), ('Cu', 30000., 'DS', 'classical')])
+def test_C5_sweep_cells(name, E0, mode, model):
+    """Six cells of BASELINE's C5 sweep (E0 x material x {continuous JL, continuous explicit, DS}) with the sweep's
+    stated parameters: tilt 70, Emin = max(500 eV, 0.05 E0) for continuous and E0/2 for DS, maxScatt 10000, default
+    table tolerances for DS.  Same checks as the named configurations."""
+    from mcdiscrete_b200.probTables import genTables
+    Emin = max(500., 0.05 * E0) if mode == 'cont' else E0 / 2
+    ip = dict(E0=E0, Emin=Emin, material=name, s_tilt=70., thickness=3e6, mode=mode, Bethe_model=model, maxScatt=10000,
+              Wc=10., tol_E=1e-4, tol_W=1e-7, electron_output=['outcome', 'final_E', 'final_dir', 'last_pos'],
+              scatter_output=[], seed=5150, elastic='Ruth_vanilla')
+    tabs = _oracle_tables_default(ip) if mode == 'DS' else None
+    eng = _engine(ip)
+    if mode == 'DS':
+        genTables(ip, engine=eng)
+    n_gpu, n_ref = 200000, 40000
+    nt = os.cpu_count() or 1
+    res = eng.run(count=n_gpu, first_id=0)
+    ref = oc.run(ip, 0, n_ref, 4243, tabs, nthreads=nt)
+    _compare(res, ref, n_gpu, n_ref, lambda: oc.run(ip, 0, n_ref, 2025, tabs, nthreads=nt))
+    ev_g = res.counters['events'] / n_gpu
+    assert abs(ev_g - ref['n_ev'].mean()) < 0.01 * ref['n_ev'].mean()
+    same = oc.run(ip, 0, 10000, 5150, tabs, nthreads=nt)
+    agree = (res.outcome[:10000] == same['outcome']).mean()
+    print('C5 %s %g eV %s %s: %.1f events per electron, same-seed outcome agreement %.5f' % (name, E0, mode, model, ev_g, agree))
+    assert agree > 0.995, agree
     eng.close()
 
 

@@ -93,6 +93,34 @@ def test_table_axes_and_rows_mid(key):
     assert np.array_equal(tabs['Gryz'][0].table[g['gryz0_rows_idx']], g['gryz0_rows'])
 
 
+@pytest.mark.parametrize('key', ['C2_Si', 'C3_Cu', 'C4_Au'])
+def test_table_axes_and_rows_default_tolerance(key):
+    """BASELINE's DEFAULT tolerances (tol_E 1e-4, tol_W 1e-7): axes (SHA-1 of the float32 arrays) and eight rows per
+    table bit-exact against the reference's own probTable (oracle/gen_golden_defaults.py), and pickTable on those
+    rows."""
+    import hashlib
+    ax = json.load(open(os.path.join(GOLD, 'table_axes_default.json')))[key]
+    g = load('tablerows_%s_default.npz' % key)
+    ip = ax['input']
+    mat = o.Material(ip['material'])
+    sha = lambda a: hashlib.sha1(np.ascontiguousarray(a, np.float32).tobytes()).hexdigest()
+    for nm, T in (('moller', o.ProbTable('Moller', mat, (ip['Emin'], ip['E0']), ip['tol_E'], ip['tol_W'], Wc=ip['Wc'])),
+                  ('gryz0', o.ProbTable('Gryzinski', mat, (ip['Emin'], ip['E0']), ip['tol_E'], ip['tol_W'],
+                                        shell=mat.name_s[-1]))):
+        T.set_axes()
+        a = ax[nm]
+        assert [T.shell, len(T.Es), len(T.Ws)] == [a['shell'], a['nE'], a['nW']]
+        assert sha(T.Es) == a['Es_sha1'] and sha(T.Ws) == a['Ws_sha1']
+        idx = g[nm + '_rows_idx']
+        rows, _ = T.compute_rows(T.Es[idx])
+        assert np.array_equal(rows, g[nm + '_rows'])
+        # pickTable on the stored rows (sparse table: only those rows exist)
+        T.table = {int(i): rows[k] for k, i in enumerate(idx)}
+        T.masked = {int(i): rows[k] == 0 for k, i in enumerate(idx)}
+        W = [o.pick_table(T, float(E), float(u))[0] for E, u in zip(g[nm + '_lookup_E'], g[nm + '_lookup_u'])]
+        assert np.array_equal(np.asarray(W, dtype=np.float64), g[nm + '_lookup_W'])
+
+
 def _tables_from_golden(key, mat):
     g = load('tables_%s.npz' % key) if not key.endswith('.npz') else load(key)
     out = {}
