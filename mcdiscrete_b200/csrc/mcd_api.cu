@@ -447,9 +447,25 @@ int alloc_table(mcd_ctx* c, int slot, const float* Es, uint32_t nE, const float*
   h.nW = nW;
   refresh_tables(c);
   DevTable& d = c->P.tab[slot];
+  // axes must be strictly increasing (bisect_left semantics, scattering.py:78,89)
+  for (uint32_t i = 1; i < nE; ++i)
+    if (!(Es[i] > Es[i - 1])) return fail(c, MCD_ERR_INVALID, "table %d: Es is not strictly increasing at %u", slot, i);
+  for (uint32_t i = 1; i < nW; ++i)
+    if (!(Ws[i] > Ws[i - 1])) return fail(c, MCD_ERR_INVALID, "table %d: Ws is not strictly increasing at %u", slot, i);
   d.E_lo = Es[0];
   d.E_hi = Es[nE - 1];
   d.inv_dE = (float)((double)(nE - 1) / ((double)Es[nE - 1] - (double)Es[0]));
+  // table_row() guesses the row as ceil((E - E_lo) * inv_dE - 0.01) and corrects UPWARD by at most one.  With
+  // Es[i] = E_lo + (i + d_i) dE and a float32 guess that is off by e cells, the guess is never above the answer iff
+  // max|d_i| + e <= 0.01, and never more than one below it.  Both are bounded here (e <= max|E| 2^-23 / dE); any
+  // other axis (non-uniform, or finer than float32 resolves) is searched by a real bisection of Es[].
+  {
+    const double dE = ((double)Es[nE - 1] - (double)Es[0]) / (double)(nE - 1);
+    double worst = 0.0;
+    for (uint32_t i = 0; i < nE; ++i) worst = fmax(worst, fabs(((double)Es[i] - (double)Es[0]) / dE - (double)i));
+    const double guess_err = fmax(fabs((double)Es[nE - 1]), fabs((double)Es[0])) * 1.2e-7 / dE;
+    d.es_uniform = (worst + guess_err < 0.009) ? 1 : 0;
+  }
   // Is Es exactly numpy.linspace(start, stop, nE, dtype=float32) for the (start, stop) the reference would use
   // (probTables.py:137-142, 364-379)?  Then the device regenerates grid values instead of loading them.
   d.es_analytic = 0;
@@ -545,6 +561,10 @@ int mcd_create(const mcd_params* p, const mcd_material* m, int device, mcd_ctx**
   if (p->mode == MCD_MODE_DS && !(p->Emin > m->plasmon_e))
     return fail(nullptr, MCD_ERR_INVALID, "DS needs Emin > plasmon energy (quinn_sigma, crossSections.py:272-281)");
   if (p->maxScatt < 0) return fail(nullptr, MCD_ERR_INVALID, "maxScatt < 0");
+  // the event index of a scats row, of a parked electron and of the regrouping key is a 24-bit field
+  if (p->maxScatt >= (1 << 24))
+    return fail(nullptr, MCD_ERR_INVALID, "maxScatt = %lld: at most 2^24 - 1 events per electron (24-bit event index)",
+                (long long)p->maxScatt);
   int n = 0;
   int rc = mcd_device_count(&n);
   if (rc != MCD_OK) return rc;

@@ -65,22 +65,25 @@ def main(argv=None):
     names = eng.material.channel_names
     t0 = time.time()
     events = 0
-    import numpy as np
-    total = None
+    import torch
+    # every rank joins the one all-reduce of the run, also a rank whose id range is empty (num_el < WORLD_SIZE)
+    total = torch.zeros_like(eng.stats_tensor())
     with ResultStore(path, inputPar, fmt) as st:
+        if st.fmt == 'h5lite' and rank == 0:
+            print(' ! PyTables is not installed: writing the HDF5 store with the self-contained writer '
+                  '(mcdiscrete_b200/h5lite.py).  Its files follow the pandas format="table" layout but have not been '
+                  'opened by libhdf5 / pandas on this machine; use --format parquet if in doubt.', file=sys.stderr)
         for first in range(lo, lo + n, batch):
             cnt = min(batch, lo + n - first)
             res = eng.run(count=cnt, first_id=first, pinned=True, ordered='columns')
             events += res.counters['events']
             st.append_result(res, names, double_record=bool(inputPar.get('reference_double_record', False)))
-            s = eng.stats_tensor().clone()
-            total = s if total is None else total + s
-    if total is not None:
-        allreduce_stats(total)
+            total += eng.stats_tensor()
+    allreduce_stats(total)
     dt = time.time() - t0
     if rank == 0:
         from . import _lib
-        h = eng.split_hist(total[:_lib.HIST_TOTAL].cpu().numpy()) if total is not None else {}
+        h = eng.split_hist(total[:_lib.HIST_TOTAL].cpu().numpy())
         stats = {'electrons': int(inputPar['num_el']), 'tables_s': t_tab, 'run_s': dt, 'ranks': world,
                  'histograms': {k: {'counts': v[0].tolist(), 'edges': v[1].tolist()} for k, v in h.items()}}
         json.dump(stats, open(path.replace('.rank0', '') + '.stats.json', 'w'))

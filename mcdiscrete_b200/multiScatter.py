@@ -27,17 +27,31 @@ from .material import material as Material
 _engines = {}
 
 
+def _run_key(inputPar, material, thingsToSave):
+    """Every field that feeds mcd_params / mcd_material (Engine.__init__): two calls with different keys must never
+    share a context."""
+    from .engine import elastic_kind
+    ds = 'DS' in inputPar['mode']
+    prm = material.params
+    mat_key = (getattr(material, 'species', inputPar['material']), prm['Z'], prm['n_val'], prm['E_val'],
+               tuple(prm['name_s']), tuple(float(prm['Es'][s]) for s in prm['name_s']),
+               tuple(float(prm['ns'][s]) for s in prm['name_s']), float(prm.get('bethe_k', 0.0)),
+               float(material.atnd), float(material.fermi_e), float(material.plasmon_e))
+    return (mat_key, 'DS' if ds else 'cont', inputPar.get('Bethe_model', 'classical') if not ds else None,
+            elastic_kind(inputPar.get('elastic', 'Ruth_vanilla'), ds),
+            float(inputPar['E0']), float(inputPar['Emin']), float(inputPar['s_tilt']),
+            float(inputPar.get('thickness', 3e6)), int(inputPar['maxScatt']), float(inputPar.get('Wc', 10.)),
+            float(inputPar.get('tol_E', 0)), float(inputPar.get('tol_W', 0)),
+            tuple(thingsToSave['el_output']), tuple(thingsToSave['scat_output']), inputPar.get('seed'))
+
+
 def _engine_for(inputPar, material, thingsToSave, tables=None):
+    key = _run_key(inputPar, material, thingsToSave)
     if tables:
         for T in [tables.get('Moller')] + list(tables.get('Gryz', [])):
             eng = getattr(T, 'engine', None)
-            if eng is not None and _compatible(eng, inputPar, thingsToSave):
+            if eng is not None and _compatible(eng, key):
                 return eng
-    key = (inputPar['material'], inputPar['mode'], inputPar.get('Bethe_model'), float(inputPar['E0']),
-           float(inputPar['Emin']), float(inputPar['s_tilt']), float(inputPar.get('thickness', 3e6)),
-           int(inputPar['maxScatt']), float(inputPar.get('Wc', 10.)), float(inputPar.get('tol_E', 0)),
-           float(inputPar.get('tol_W', 0)), tuple(thingsToSave['el_output']), tuple(thingsToSave['scat_output']),
-           inputPar.get('seed'))
     eng = _engines.get(key)
     if eng is None:
         ip = dict(inputPar, electron_output=list(thingsToSave['el_output']),
@@ -58,10 +72,14 @@ def _engine_for(inputPar, material, thingsToSave, tables=None):
     return eng
 
 
-def _compatible(eng, inputPar, thingsToSave):
-    ip = eng.inputPar
-    same = all(ip.get(k) == inputPar.get(k) for k in ('material', 'mode', 'E0', 'Emin', 's_tilt', 'maxScatt', 'Wc'))
-    return same and eng.el_cols == list(thingsToSave['el_output']) and eng.scat_cols == list(thingsToSave['scat_output'])
+def _compatible(eng, key):
+    """The engine the tables were built on may be reused only if it was created from the same parameters (elastic
+    model, thickness, Bethe model, seed and tolerances included) and the same material."""
+    try:
+        return eng.gryz_mode == 'outermost' and \
+            _run_key(eng.inputPar, eng.material, {'el_output': eng.el_cols, 'scat_output': eng.scat_cols}) == key
+    except (KeyError, NotImplementedError):
+        return False
 
 
 def _per_electron_dicts(eng, res, inputPar, thingsToSave):

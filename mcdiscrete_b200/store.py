@@ -94,7 +94,27 @@ def scats_frame(res, inputPar, channel_names, sort=True):
     return pd.DataFrame(data, columns=out_cols)
 
 
-STR_WIDTH = 16       # longest labels: 'Gryz3s3p3d', 'Ruth_nigram_wDefl' (the reference's min_itemsize=6 truncates them)
+def _label_width():
+    """Width of the string columns: the longest label they can hold -- outcome names, channel names of every
+    material ('Gryz3s3p3d') and, in continuous mode, the elastic label ('Ruth_vanilla_wDefl', 18 characters).  The
+    reference's min_itemsize = 6 truncates most of them."""
+    from .engine import ELASTIC_MODELS
+    from .material import material, _SPECIES as SPECIES
+    w = max(len(x) for x in tuple(_lib.OUTCOMES) + tuple(ELASTIC_MODELS))
+    for sp in SPECIES:
+        w = max([w] + [len(x) for x in material(sp).channel_names])
+    return max(w, 18)
+
+
+STR_WIDTH = _label_width()
+
+
+def _as_label(value, n):
+    """n copies of a label as fixed-width bytes; refuses to truncate."""
+    b = str(value).encode()
+    if len(b) > STR_WIDTH:
+        raise ValueError('label %r is longer than the %d-byte string column' % (value, STR_WIDTH))
+    return np.full(n, b, dtype='S%d' % STR_WIDTH)
 
 
 def els_columns(res, inputPar, double_record=False):
@@ -128,7 +148,7 @@ def scats_columns(res, inputPar, channel_names, sort=True):
     for c in flat_columns(req, 'scats'):
         if c == 'type':
             if cont:
-                out[c] = np.full(len(sc), inputPar.get('elastic', 'Ruth_vanilla').encode(), dtype='S%d' % STR_WIDTH)
+                out[c] = _as_label(inputPar.get('elastic', 'Ruth_vanilla'), len(sc))
             else:
                 out[c] = np.array(channel_names, dtype='S%d' % STR_WIDTH)[sc['type']]
         elif c == 'direction':
@@ -232,13 +252,17 @@ class ResultStore:
         if len(df) == 0:
             return
         if self.fmt == 'h5lite':
-            self.append_columns(key, {c: (np.asarray(df[c].astype(str).str.encode('utf-8'), dtype='S%d' % STR_WIDTH)
-                                          if df[c].dtype == object or str(df[c].dtype).startswith('str')
+            def fixed(col):
+                b = col.astype(str).str.encode('utf-8')
+                if len(b) and int(b.str.len().max()) > STR_WIDTH:
+                    raise ValueError('a label of column %r is longer than the %d-byte string column' % (col.name, STR_WIDTH))
+                return np.asarray(b, dtype='S%d' % STR_WIDTH)
+            self.append_columns(key, {c: (fixed(df[c]) if df[c].dtype == object or str(df[c].dtype).startswith('str')
                                           else np.asarray(df[c])) for c in df.columns})
             return
         if self.fmt == 'hdf5':
             # widths of the longest labels (the reference's min_itemsize=6 truncates 'Gryz2s2p', doScatter.py:75-79)
-            sizes = {c: 16 for c in df.columns if df[c].dtype == object}
+            sizes = {c: STR_WIDTH for c in df.columns if df[c].dtype == object}
             self.store.put(key, df, format='table', data_columns=True, append=True, min_itemsize=sizes)
         else:
             import pyarrow as pa

@@ -174,3 +174,37 @@ def test_host_axis_search_default_tolerance(key):
         assert T.Es.dtype == np.float32 and T.Ws.dtype == np.float32
         assert sha(T.Es) == a['Es_sha1'] and sha(T.Ws) == a['Ws_sha1']
         assert not T.exhausted
+
+
+def test_argument_checks_precede_the_device(lib):
+    """mcd_create rejects what the packed row format cannot hold before it touches a device: the event index of a
+    scats row / parked electron is a 24-bit field, so maxScatt >= 2^24 is MCD_ERR_INVALID (not silent corruption)."""
+    from mcdiscrete_b200 import _lib
+    from mcdiscrete_b200.engine import Engine
+    ip = dict(E0=2e4, Emin=1e4, material='Si', s_tilt=70., mode='DS')
+    for bad in (1 << 24, 10 ** 9):
+        with pytest.raises(_lib.MCDError) as ei:
+            Engine(dict(ip, maxScatt=bad))
+        assert ei.value.code == -1 and '24-bit' in str(ei.value)
+
+
+def test_multiScatter_engine_key_covers_every_parameter():
+    """Two worker calls that differ in ANY field feeding mcd_params / mcd_material must not share a context."""
+    from mcdiscrete_b200.material import material
+    from mcdiscrete_b200.multiScatter import _run_key
+    tts = {'el_output': ['outcome'], 'scat_output': []}
+    ip = dict(E0=2e4, Emin=1e4, material='Si', s_tilt=70., maxScatt=1000, mode='DS', elastic='Ruth_vanilla',
+              thickness=3e6, Wc=10., tol_E=1e-2, tol_W=1e-3, seed=1, Bethe_model='classical')
+    mat = material('Si')
+    base = _run_key(ip, mat, tts)
+    for k, v in dict(elastic='Ruth_nigram', thickness=2000., seed=2, tol_E=1e-3, tol_W=1e-4, Wc=20., maxScatt=10,
+                     s_tilt=0., Emin=5e3, E0=3e4, mode='cont').items():
+        assert _run_key(dict(ip, **{k: v}), mat, tts) != base, k
+    assert _run_key(ip, material('Cu'), tts) != base                       # the material OBJECT, not inputPar['material']
+    m2 = material('Si'); m2.params['Es']['2p'] = 101.
+    assert _run_key(ip, m2, tts) != base
+    assert _run_key(ip, mat, {'el_output': ['outcome'], 'scat_output': ['type']}) != base
+    c = dict(ip, mode='cont')
+    assert _run_key(dict(c, Bethe_model='JL'), mat, tts) != _run_key(c, mat, tts)
+    # continuous mode: the _wDefl labels run the plain forms (scattering.py:781-789) -> same physics, same key
+    assert _run_key(dict(c, elastic='Ruth_vanilla_wDefl'), mat, tts) == _run_key(c, mat, tts)

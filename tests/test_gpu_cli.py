@@ -216,3 +216,66 @@ def test_top_level_run():
     assert np.array_equal(a.els, b.els) and np.array_equal(a.scats['energy'], b.scats['energy'])
     c = mcd.run(dict(ip, mode='cont', Emin=2000.), seed=7, device=0, count=500)
     assert c.count == 500 and set(np.unique(c.outcome)) <= {0, 1, 2, 4}
+
+
+def test_workers_do_not_reuse_a_context_across_changed_parameters():
+    """Two worker calls in one process that differ only in `elastic` or `thickness` (fields the round-1 engine cache
+    ignored) must run with their own parameters -- also when the tables handed in were built on the first engine."""
+    from mcdiscrete_b200 import material, genTables, multiTraj_DS
+    from mcdiscrete_b200.engine import Engine
+    ip = dict(num_el=4000, E0=20000., Emin=15000., material='Si', s_tilt=0., thickness=3e6, elastic='Ruth_vanilla',
+              mode='DS', Bethe_model='classical', diffMFP=False, gen_tables=True, tol_E=1e-2, tol_W=1e-3,
+              maxScatt=1000, Wc=10., electron_output=['outcome', 'final_E'], scatter_output=[], seed=99)
+    what = {'el_output': ip['electron_output'], 'scat_output': []}
+    mat = material('Si')
+    tables = genTables(ip)                                      # built on an engine created from `ip`
+    n = 4000
+
+    def fractions(res):
+        o = [r['els']['outcome'][0] for r in res]
+        return {k: o.count(k) / len(o) for k in ('abs', 'bks', 'trsm')}
+    thick = fractions(multiTraj_DS(ip, n, mat, tables, what))
+    thin = fractions(multiTraj_DS(dict(ip, thickness=1500.), n, mat, tables, what))
+    assert thick['trsm'] == 0 and thin['trsm'] > 0.5             # a 150 nm film transmits most 20 keV electrons
+    nig = fractions(multiTraj_DS(dict(ip, elastic='Ruth_nigram', s_tilt=70.), n, mat, tables, what))
+    van = fractions(multiTraj_DS(dict(ip, s_tilt=70.), n, mat, tables, what))
+    # reference numbers for the two models from dedicated engines on the same ids
+    want = {}
+    for el in ('Ruth_nigram', 'Ruth_vanilla'):
+        e = Engine(dict(ip, elastic=el, s_tilt=70.), device=0)
+        genTables(dict(ip, elastic=el, s_tilt=70.), engine=e)
+        want[el] = float((e.run(count=n, first_id=0).outcome == 1).mean())
+        e.close()
+    assert abs(nig['bks'] - want['Ruth_nigram']) < 1e-12 and abs(van['bks'] - want['Ruth_vanilla']) < 1e-12
+    assert abs(want['Ruth_nigram'] - want['Ruth_vanilla']) > 0.01
+
+
+def test_non_uniform_energy_axis_is_bisected():
+    """mcd_table_upload accepts any strictly increasing Es; an axis that is not the uniform grid the row guess assumes
+    (or is finer than float32 resolves) must be searched by bisection: rows identical to bisect_left."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import mcd_oracle as o
+    from mcdiscrete_b200 import _lib
+    from mcdiscrete_b200.engine import Engine
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'tables_Si_15k_small.npz'))
+    ip = dict(E0=20000., Emin=15000., material='Si', s_tilt=70., maxScatt=1000, mode='DS', scatter_output=[])
+    eng = Engine(ip, device=0)
+    rng = np.random.default_rng(5)
+    nE = len(g['moller_Es'])
+    for Es in (np.sort(rng.uniform(15000., 20000., nE)).astype(np.float32),                  # irregular
+               np.geomspace(15000., 20000., nE).astype(np.float32),                          # geometric
+               (15000. + 5000. * np.linspace(0, 1, nE) ** 2).astype(np.float32)):            # quadratic
+        Es[0], Es[-1] = 15000., 20000.
+        assert (np.diff(Es) > 0).all()
+        eng.table_upload(0, Es, g['moller_Ws'], g['moller_table'])
+        E = np.concatenate([rng.uniform(15000.1, 20000., 4000), Es[1:], np.nextafter(Es[1:], np.float32(0)),
+                            np.nextafter(Es[:-1], np.float32(1e9))]).astype(np.float32)
+        u = np.clip(rng.random(len(E)), 2.0 ** -24, 1 - 2.0 ** -24).astype(np.float32)
+        W, iE, jW = eng.test_lookup(0, E, u)
+        assert np.array_equal(iE, np.searchsorted(Es, E, side='left'))
+    with pytest.raises(_lib.MCDError) as ei:                    # not increasing: rejected
+        bad = g['moller_Es'].copy(); bad[3] = bad[2]
+        eng.table_upload(0, bad, g['moller_Ws'], g['moller_table'])
+    assert ei.value.code == -1
+    eng.close()

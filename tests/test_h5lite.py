@@ -183,7 +183,7 @@ def test_store_writes_the_pandas_frame_table_contract(tmp_path):
     """What pandas.HDFStore.put(key, df, format='table', data_columns=True) leaves in a file (io/pytables.py:
     set_object_info, Table.set_attrs, IndexCol/DataCol.set_attr) and PyTables adds for a Table."""
     from test_store_cli import _fake_result, IP, NAMES
-    from mcdiscrete_b200.store import ResultStore, read_store
+    from mcdiscrete_b200.store import ResultStore, read_store, STR_WIDTH
     res, rows = _fake_result()
     path = str(tmp_path / 'run.h5')
     with ResultStore(path, IP, fmt='hdf5', chunk_rows=4) as st:
@@ -210,7 +210,7 @@ def test_store_writes_the_pandas_frame_table_contract(tmp_path):
             assert t.attr('FIELD_%d_NAME' % i) == n
         for c in cols:
             assert t.attr(c + '_kind') == [c] and t.attr(c + '_meta') is None
-            assert t.attr(c + '_dtype') == ('bytes128' if c in ('outcome', 'type') else 'float64')
+            assert t.attr(c + '_dtype') == ('bytes%d' % (8 * STR_WIDTH) if c in ('outcome', 'type') else 'float64')
         assert np.array_equal(t.read()['index'], np.arange(t.shape[0]))
     back = read_store(path)
     assert back['input']['material'] == 'Si' and back['input']['num_el'] == '5'

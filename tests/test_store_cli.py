@@ -117,3 +117,27 @@ def test_columnar_scats_view_equals_row_view(tmp_path):
         assert open(a, 'rb').read() == open(b, 'rb').read()  # the self-contained writer is deterministic
     ra, rb = read_store(a), read_store(b)
     assert ra['scats'].equals(rb['scats']) and ra['els'].equals(rb['els'])
+
+
+@pytest.mark.parametrize('elastic', ['Ruth_vanilla_wDefl', 'Ruth_nigram_wDefl'])
+def test_continuous_mode_elastic_labels_are_stored_in_full(tmp_path, elastic):
+    """In continuous mode the scats `type` column holds the elastic label (scattering.py:802-840); the longest ones
+    ('Ruth_vanilla_wDefl', 18 characters) must survive the fixed-width string column of the HDF5 store."""
+    from mcdiscrete_b200.store import STR_WIDTH, scats_columns
+    assert STR_WIDTH >= 18
+    res, rows = _fake_result()
+    ip = dict(IP, mode='cont', elastic=elastic, scatter_output=['type', 'energy'])
+    # continuous rows: words [rel_id, ev|0<<24, energy]
+    sr = res.sorted_scats()
+    w = np.ascontiguousarray(sr.words[:, [0, 1, 5]])
+    word_of = [1, -1, -1, -1, -1, -1, -1, 2, -1] + [-1] * 7
+    res_c = RunResult(res.first_id, res.count, res.els, ScatRows(w, word_of, sr.first_id, sr.offsets), {}, 0.0)
+    cols = scats_columns(res_c, ip, [elastic])
+    assert set(cols['type'].tolist()) == {elastic.encode()}
+    path = str(tmp_path / 'cont.h5')
+    with ResultStore(path, ip, fmt='hdf5') as st:
+        st.append_result(res_c, [elastic])
+    back = read_store(path)
+    assert set(back['scats']['type']) == {elastic}
+    with pytest.raises(ValueError):
+        scats_columns(res_c, dict(ip, elastic='x' * (STR_WIDTH + 1)), [elastic])
