@@ -226,6 +226,10 @@ int mcd_hist_get(mcd_ctx* ctx, int64_t* host /* MCD_HIST_TOTAL */);
 /* Device address of the int64 histogram||counter block, for an in-place NCCL all-reduce by the caller
  * (the only collective of the path).  n_int64 = MCD_HIST_TOTAL + sizeof(mcd_counters)/8. */
 int mcd_stats_device_ptr(mcd_ctx* ctx, void** dev_ptr, uint64_t* n_int64);
+/* dst's histogram||counter block += src's, and src's block is cleared, on `stream` (which must be ordered after the
+ * runs of both contexts): the contexts of a pipeline (mcd_clone) are merged into one block before the single
+ * all-reduce of a multi-GPU run. */
+int mcd_stats_merge(mcd_ctx* dst, mcd_ctx* src, void* stream);
 /* Histogram axis ranges: energy [Emin,E0], polar [0,90] deg, azimuth [-180,180) deg, depth [0,depth_max] A. */
 int mcd_hist_ranges(const mcd_ctx* ctx, double* e_lo, double* e_hi, double* depth_max);
 /* Timing of the last mcd_run's trajectory kernel in ms (CUDA events on the launch stream). */

@@ -92,6 +92,7 @@ SYMBOLS = {
     'mcd_counters_get': (C.c_int, [_P, C.POINTER(Counters)]),
     'mcd_hist_get': (C.c_int, [_P, C.POINTER(C.c_int64)]),
     'mcd_stats_device_ptr': (C.c_int, [_P, C.POINTER(_P), C.POINTER(_U64)]),
+    'mcd_stats_merge': (C.c_int, [_P, _P, _P]),
     'mcd_hist_ranges': (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     'mcd_last_kernel_ms': (C.c_int, [_P, C.POINTER(C.c_float)]),
     'mcd_launch_info': (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),

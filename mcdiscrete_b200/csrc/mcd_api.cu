@@ -1070,6 +1070,14 @@ int mcd_stats_device_ptr(mcd_ctx* c, void** dev_ptr, uint64_t* n_int64) {
   return MCD_OK;
 }
 
+int mcd_stats_merge(mcd_ctx* dst, mcd_ctx* src, void* stream) {
+  int rc = need_ctx(dst);
+  if (rc) return rc;
+  if (!src || src == dst || src->device != dst->device) return fail(dst, MCD_ERR_INVALID, "merge needs a second context on the same device");
+  CU(dst, mcd_launch_stats_merge(dst->stats, src->stats, (int)kStatsWords, (cudaStream_t)stream));
+  return MCD_OK;
+}
+
 int mcd_hist_ranges(const mcd_ctx* c, double* e_lo, double* e_hi, double* depth_max) {
   if (!c) return fail(nullptr, MCD_ERR_INVALID, "null context");
   if (e_lo) *e_lo = c->par.Emin;

@@ -27,6 +27,7 @@ struct TrajLaunchInfo {
 cudaError_t mcd_launch_traj(const DevParams& P, const DevOut& O, unsigned long long first_id,
                             unsigned long long count, int sm_count, cudaStream_t stream, TrajLaunchInfo* info);
 cudaError_t mcd_traj_max_blocks(const DevParams& P, bool scats, int sm_count, TrajLaunchInfo* info);
+cudaError_t mcd_launch_stats_merge(unsigned long long* dst, unsigned long long* src, int n, cudaStream_t stream);
 int mcd_traj_uses_queue(const DevParams& P, bool scats);     // 1 if mcd_launch_traj wants the leftover queues
 
 cudaError_t mcd_launch_order_scats(const unsigned int* nev, unsigned long long count, unsigned long long* tile_tmp,

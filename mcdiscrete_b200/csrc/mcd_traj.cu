@@ -70,10 +70,11 @@ __device__ __forceinline__ void store_scat_row(uint32_t* __restrict__ dst, uint3
 }
 
 // saveOutcomes (electron.py:105-113) of a lane whose trajectory ended: the 32-byte els row (one full sector, two
-// 16-byte stores), outcome / event counters and, for 'bks', the fused backscatter histograms.  preE = energy before
-// the event's loss; e = direction before the event's rotation, position as update_xyz left it.
-__device__ __forceinline__ void retire_lane(const DevParams& P, const DevOut& O, unsigned int* s_hist,
-                                            unsigned int* s_cnt, bool want_hist, int outcome, bool dbl,
+// 16-byte stores) and the outcome / event counters.  preE = energy before the event's loss; e = direction before the
+// event's rotation, position as update_xyz left it.  The backscatter histograms are NOT built here: they
+// are a function of the els row alone and are binned by hist_kernel in one pass over the rows after the last launch
+// of the run (no acosf / atan2f code, 6 KB of shared memory and 1564-bin flush per block in the trajectory kernels).
+__device__ __forceinline__ void retire_lane(const DevOut& O, unsigned int* s_cnt, int outcome, bool dbl,
                                             float preE, const ElState& e, uint32_t rel_id, uint32_t nev) {
   float4* dst = reinterpret_cast<float4*>(O.els + rel_id);
   dst[0] = make_float4(__uint_as_float((uint32_t)outcome | (dbl ? 0x100u : 0u)), preE, e.dx, e.dy);
@@ -84,29 +85,11 @@ __device__ __forceinline__ void retire_lane(const DevParams& P, const DevOut& O,
   atomicAdd(&s_cnt[kCntDone], 1u);
   if (atomicAdd(&s_cnt[kCntEvents], nev) + nev < nev) atomicAdd(&s_cnt[kCntEventsHi], 1u);
   if (dbl) atomicAdd(&s_cnt[kCntDouble], 1u);
-  if (want_hist && outcome == MCD_OUT_BKS) {
-    int b = (int)((preE - P.hist.e_lo) * P.hist.e_scale);
-    b = max(0, min(b, MCD_HIST_E_BINS - 1));
-    atomicAdd(&s_hist[b], 1u);
-    const float pol = acosf(fminf(1.0f, fmaxf(-1.0f, -e.dz))) * 57.29577951308232f;       // from -z normal
-    b = max(0, min((int)(pol * 2.0f), MCD_HIST_POLAR_BINS - 1));
-    atomicAdd(&s_hist[MCD_HIST_E_BINS + b], 1u);
-    const float az = atan2f(e.dy, e.dx) * 57.29577951308232f + 180.0f;
-    b = max(0, min((int)az, MCD_HIST_AZ_BINS - 1));
-    atomicAdd(&s_hist[MCD_HIST_E_BINS + MCD_HIST_POLAR_BINS + b], 1u);
-    b = max(0, min((int)(e.z * P.hist.depth_scale), MCD_HIST_DEPTH_BINS - 1));
-    atomicAdd(&s_hist[MCD_HIST_E_BINS + MCD_HIST_POLAR_BINS + MCD_HIST_AZ_BINS + b], 1u);
-  }
 }
 
-// block statistics -> global stats block (histograms || mcd_counters), once per block
-__device__ __forceinline__ void flush_block_stats(const DevOut& O, const unsigned int* s_hist,
-                                                  const unsigned int* s_cnt, const unsigned long long* s_rows,
-                                                  bool want_scats, bool want_chan) {
-  for (int i = threadIdx.x; i < MCD_HIST_TOTAL; i += blockDim.x) {
-    const unsigned int v = s_hist[i];
-    if (v) atomicAdd(O.stats + i, (unsigned long long)v);
-  }
+// block counters -> global stats block (histograms || mcd_counters), once per block
+__device__ __forceinline__ void flush_block_stats(const DevOut& O, const unsigned int* s_cnt,
+                                                  const unsigned long long* s_rows, bool want_scats, bool want_chan) {
   unsigned long long* cnt = O.stats + MCD_HIST_TOTAL;
   // mcd_counters layout: electrons_done, events, outcome[5], double_records, stored, dropped, nan, exact, channel[]
   if (threadIdx.x == 0) {
@@ -126,15 +109,57 @@ __device__ __forceinline__ void flush_block_stats(const DevOut& O, const unsigne
   }
 }
 
+// Backscatter histograms of one run from its els rows (final energy 512 bins [Emin, E0], exit polar
+// angle from the surface normal 180 bins [0, 90] deg, exit azimuth 360 bins, last interior depth 512 bins [0, 2R]).
+// One pass over 32 bytes per electron (HBM-bound: ~5 us per 1e6 electrons), block histograms in shared memory,
+// one 64-bit atomic per non-empty bin and block.
+__global__ void __launch_bounds__(256) hist_kernel(const DevHistSpec H, const mcd_el_row* __restrict__ els,
+                                                   const unsigned long long count, unsigned long long* __restrict__ stats) {
+  __shared__ unsigned int s_hist[MCD_HIST_TOTAL];
+  for (int i = threadIdx.x; i < MCD_HIST_TOTAL; i += blockDim.x) s_hist[i] = 0u;
+  __syncthreads();
+  const float4* rows = reinterpret_cast<const float4*>(els);
+  for (unsigned long long r = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; r < count;
+       r += (unsigned long long)gridDim.x * blockDim.x) {
+    const float4 a = __ldcs(rows + 2 * r);               // code, final_E, dx, dy
+    if ((__float_as_uint(a.x) & 0xffu) != (uint32_t)MCD_OUT_BKS) continue;
+    const float4 b = __ldcs(rows + 2 * r + 1);           // dz, last_x, last_y, last_z
+    int k = (int)((a.y - H.e_lo) * H.e_scale);
+    k = max(0, min(k, MCD_HIST_E_BINS - 1));
+    atomicAdd(&s_hist[k], 1u);
+    const float pol = acosf(fminf(1.0f, fmaxf(-1.0f, -b.x))) * 57.29577951308232f;       // from the -z normal
+    k = max(0, min((int)(pol * 2.0f), MCD_HIST_POLAR_BINS - 1));
+    atomicAdd(&s_hist[MCD_HIST_E_BINS + k], 1u);
+    const float az = atan2f(a.w, a.z) * 57.29577951308232f + 180.0f;
+    k = max(0, min((int)az, MCD_HIST_AZ_BINS - 1));
+    atomicAdd(&s_hist[MCD_HIST_E_BINS + MCD_HIST_POLAR_BINS + k], 1u);
+    k = max(0, min((int)(b.w * H.depth_scale), MCD_HIST_DEPTH_BINS - 1));
+    atomicAdd(&s_hist[MCD_HIST_E_BINS + MCD_HIST_POLAR_BINS + MCD_HIST_AZ_BINS + k], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < MCD_HIST_TOTAL; i += blockDim.x) {
+    const unsigned int v = s_hist[i];
+    if (v) atomicAdd(stats + i, (unsigned long long)v);
+  }
+}
+
+// dst += src; src = 0 (both histogram || counter blocks): the contexts of a pipeline are merged into one block
+// before the run's single all-reduce
+__global__ void stats_merge_kernel(unsigned long long* __restrict__ dst, unsigned long long* __restrict__ src, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const unsigned long long v = src[i];
+    if (v) { dst[i] += v; src[i] = 0ull; }
+  }
+}
+
 template <int S, int MODE, bool SCATS>
 __global__ void __launch_bounds__(kThreads, MCD_MIN_BLOCKS)
 traj_kernel(const __grid_constant__ DevParams P, const DevOut O, const unsigned long long first_id,
             const unsigned long long count) {
-  __shared__ unsigned int s_hist[MCD_HIST_TOTAL];
   __shared__ unsigned int s_cnt[kCntTotal];
   __shared__ unsigned long long s_rows[2];      // stored, dropped
 
-  for (int i = threadIdx.x; i < MCD_HIST_TOTAL; i += kThreads) s_hist[i] = 0u;
   for (int i = threadIdx.x; i < kCntTotal; i += kThreads) s_cnt[i] = 0u;
   if (threadIdx.x < 2) s_rows[threadIdx.x] = 0ull;
   __syncthreads();
@@ -142,7 +167,6 @@ traj_kernel(const __grid_constant__ DevParams P, const DevOut O, const unsigned 
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lt = lanemask_lt();
   constexpr bool want_scats = SCATS;            // compile time: the no-scats kernel carries no row fields
-  const bool want_hist = (P.flags & MCD_FLAG_HISTOGRAMS) != 0u;
   const bool want_chan = (P.flags & MCD_FLAG_CHANNEL_COUNTS) != 0u;
   int chunk = -1;                                // this warp's current chunk (warp-uniform)
   unsigned int used = 0u;                        // rows already stored in it
@@ -207,7 +231,7 @@ traj_kernel(const __grid_constant__ DevParams P, const DevOut O, const unsigned 
     if (outcome >= 0) {
       const uint32_t nev = ev + (has_row ? 1u : 0u);
       if (want_scats) O.nev[rel_id] = nev;
-      retire_lane(P, O, s_hist, s_cnt, want_hist, outcome, (row.flags & MCD_EVF_DOUBLE) != 0, row.E, e, rel_id, nev);
+      retire_lane(O, s_cnt, outcome, (row.flags & MCD_EVF_DOUBLE) != 0, row.E, e, rel_id, nev);
       alive = false;
     }
     // update_direction of this event (the exit event still rotates and, if requested, records its direction)
@@ -263,7 +287,7 @@ traj_kernel(const __grid_constant__ DevParams P, const DevOut O, const unsigned 
     if (w_dropped) atomicAdd(&s_rows[1], (unsigned long long)w_dropped);
   }
   __syncthreads();
-  flush_block_stats(O, s_hist, s_cnt, s_rows, want_scats, want_chan);
+  flush_block_stats(O, s_cnt, s_rows, want_scats, want_chan);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -345,17 +369,14 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
   // are needed to give every lane two electrons (lanes + pool) do any work
   const unsigned long long count = RESUME ? *O.rq_in_count : count_arg;
   if (RESUME && (unsigned long long)blockIdx.x * (2ull * kPoolThreads) >= count) return;
-  __shared__ unsigned int s_hist[MCD_HIST_TOTAL];
   __shared__ unsigned int s_cnt[kCntTotal];
   __shared__ __align__(16) uint32_t s_pool[kPoolThreads / 32][kSlotWords * kPoolSlots];
 
-  for (int i = threadIdx.x; i < MCD_HIST_TOTAL; i += kPoolThreads) s_hist[i] = 0u;
   for (int i = threadIdx.x; i < kCntTotal; i += kPoolThreads) s_cnt[i] = 0u;
   __syncthreads();
 
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lt = lanemask_lt();
-  const bool want_hist = (P.flags & MCD_FLAG_HISTOGRAMS) != 0u;
   const bool want_chan = (P.flags & MCD_FLAG_CHANNEL_COUNTS) != 0u;
   uint32_t* const pool = s_pool[threadIdx.x >> 5];
   // warp-uniform bookkeeping in ONE register (the loop is at the register limit of 6 blocks per SM):
@@ -556,7 +577,7 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
     outcome = (absorbed && outcome < 0) ? MCD_OUT_ABS : outcome;
     e.E = En;
     if (outcome >= 0) {
-      retire_lane(P, O, s_hist, s_cnt, want_hist, outcome, dbl, preE, e, rel_id, ev + (done ? 1u : 0u));
+      retire_lane(O, s_cnt, outcome, dbl, preE, e, rel_id, ev + (done ? 1u : 0u));
       alive = false;
     }
     if (done) {
@@ -570,7 +591,7 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
 #undef n_pend
 #undef exhausted
   __syncthreads();
-  flush_block_stats(O, s_hist, s_cnt, nullptr, false, want_chan);
+  flush_block_stats(O, s_cnt, nullptr, false, want_chan);
 }
 
 typedef void (*TrajKernel)(const DevParams, const DevOut, const unsigned long long, const unsigned long long);
@@ -889,5 +910,19 @@ cudaError_t mcd_launch_traj(const DevParams& P, const DevOut& O_in, unsigned lon
     err = cudaGetLastError();
     if (err != cudaSuccess) return err;
   }
+  if (P.flags & MCD_FLAG_HISTOGRAMS) {
+    // the backscatter histograms: one pass over the els rows this run wrote
+    unsigned long long nb = (count + 256ull * 8ull - 1ull) / (256ull * 8ull);
+    const unsigned long long cap = (unsigned long long)sm_count * 8ull;
+    if (nb > cap) nb = cap;
+    hist_kernel<<<(unsigned int)(nb ? nb : 1), 256, 0, stream>>>(P.hist, O_in.els, count, O_in.stats);
+    err = cudaGetLastError();
+    if (err != cudaSuccess) return err;
+  }
   return cudaSuccess;
+}
+
+cudaError_t mcd_launch_stats_merge(unsigned long long* dst, unsigned long long* src, int n, cudaStream_t stream) {
+  stats_merge_kernel<<<(n + 255) / 256, 256, 0, stream>>>(dst, src, n);
+  return cudaGetLastError();
 }

@@ -470,15 +470,57 @@ class Engine:
         els, scats = self.drain(first_id, count, pinned=pinned, stream=stream, ordered=ordered) if drain else (None, {})
         return RunResult(first_id, count, els, scats, cnt, self.kernel_ms())
 
-    def run_batches(self, total, batch, first_id=0, max_scat_rows=None, on_launched=None, ordered=False, depth=None):
+    def pipeline_engines(self):
+        """This engine and the clones run_batches rotates over."""
+        pipe = getattr(self, '_pipe', None)
+        return [self] + (list(pipe[0]) if pipe else [])
+
+    def stats_host(self):
+        """The int64 histogram||counter block of this context, copied to the host (numpy)."""
+        return self.stats_tensor().cpu().numpy()
+
+    def merge_stats_from(self, other, stream=None):
+        """This context's histogram||counter block += `other`'s (which is cleared), on `stream` (mcd_stats_merge)."""
+        self._ck(self.lib.mcd_stats_merge(self.ctx, other.ctx, C.c_void_p(stream or 0)))
+
+    def pipeline_stats(self, device=True):
+        """The histogram||counter block of a run made of run_batches(..., accumulate=True) calls: what is all-reduced
+        ONCE at the end of the run.  Statistics-only contexts accumulate on the device over their
+        batches; the clones' blocks are merged into this context's block (mcd_stats_merge) and the returned tensor IS
+        that block (zero-copy, all-reduce it in place).  When scats rows are recorded the per-batch blocks were summed
+        by the host (run_batches) and are uploaded.  device=False returns a numpy copy instead."""
+        import torch
+        if self.row_words:
+            acc = getattr(self, '_acc_host', None)
+            tot = acc if acc is not None else np.zeros(_lib.HIST_TOTAL + C.sizeof(_lib.Counters) // 8, np.int64)
+            return torch.from_numpy(tot.copy()).to('cuda:%d' % self.device) if device else tot.copy()
+        torch.cuda.synchronize(self.device)              # every stream of the pipeline has finished its batches
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        for e in self.pipeline_engines()[1:]:
+            self.merge_stats_from(e, st)
+        t = self.stats_tensor()
+        return t if device else t.cpu().numpy()
+
+    def reset_pipeline_stats(self):
+        for e in self.pipeline_engines():
+            e.reset_stats()
+            e.sync()
+        self._acc_host = None
+
+    def run_batches(self, total, batch, first_id=0, max_scat_rows=None, on_launched=None, ordered=False, depth=None,
+                    accumulate=False, els=None):
         """Simulate `total` electrons in batches of `batch`, PIPELINED over `depth` contexts / CUDA streams
         (default 6 for statistics-only runs, 2 when scats rows are recorded): while the host drains batch k
         (D2H into pinned buffers) the next batches already run, their blocks fill the SMs that the tail of batch k
         leaves idle, and the tail hand-over passes of one batch hide behind the main pass of another.  Yields
         one RunResult per batch, in order.  Rows of a yielded result live in reused pinned buffers: consume them
         before advancing the generator `depth` times.
-        `on_launched(engine, torch_stream)` is called right after each launch (e.g. to enqueue the NCCL
-        all-reduce of engine.stats_tensor() on that stream)."""
+        `on_launched(engine, torch_stream)` is called right after each launch.
+        accumulate=True: the statistics of the batches are summed for ONE all-reduce at the end of the run
+        (pipeline_stats()): statistics-only contexts simply keep accumulating on the device (no per-batch reset, no
+        per-batch counter read; RunResult.counters is None); when scats rows are recorded the per-batch block is read
+        with the batch's counters and summed by the host.
+        els=False: the els rows stay on the device (histogram-only runs, BASELINE C4)."""
         import torch
         from collections import deque
         if self.params.mode == _lib.MODE_DS and self.tables is None:
@@ -500,21 +542,32 @@ class Engine:
             max_scat_rows = (batch * min(int(self.inputPar['maxScatt']), 512) + 65536) if self.row_words else 0
         pending = deque()
 
+        want_els = bool(self.el_cols) if els is None else bool(els)
+
         def finish(p):
             e, st, first, cnt = p
             e.sync(st)
-            cnts = e.counters()
-            if cnts['scat_rows_dropped']:
-                raise _lib.MCDError(-5, '%d scats rows did not fit: raise max_scat_rows or lower batch' % cnts['scat_rows_dropped'])
-            els, scats = e.drain(first, cnt, pinned=True, stream=st, ordered=ordered)
-            return RunResult(first, cnt, els, scats, cnts, e.kernel_ms())
+            cnts = None
+            if e.row_words or not accumulate:
+                cnts = e.counters()
+                if cnts['scat_rows_dropped']:
+                    raise _lib.MCDError(-5, '%d scats rows did not fit: raise max_scat_rows or lower batch' % cnts['scat_rows_dropped'])
+                if accumulate:
+                    blk = e.stats_host()
+                    self._acc_host = blk if getattr(self, '_acc_host', None) is None else self._acc_host + blk
+            if want_els or e.row_words:
+                els_rows, scats = e.drain(first, cnt, want_els=want_els, pinned=True, stream=st, ordered=ordered)
+            else:
+                els_rows, scats = None, {}
+            return RunResult(first, cnt, els_rows, scats, cnts, e.kernel_ms())
         k = 0
         try:
             for first in range(first_id, first_id + total, batch):
                 cnt = min(batch, first_id + total - first)
                 e, st = engs[k % depth], streams[k % depth].cuda_stream
                 e.set_capacity(max(batch, e.cap_el), max(max_scat_rows, e.cap_sc))
-                e.reset_stats(st)
+                if e.row_words or not accumulate:
+                    e.reset_stats(st)
                 e.launch(first, cnt, st)
                 if ordered == 'columns' and e.row_words:
                     # regrouping enqueued behind the kernel: it overlaps the D2H drain of the previous batch
