@@ -33,6 +33,13 @@ def _worker(rank, world, port, q):
     mine = local.clone()
     allreduce_stats(local)
     lo, cnt = rank_range(1001, rank, world)
+    # a job with fewer electrons than ranks: the rank whose id range is empty still joins the run's ONE all-reduce
+    # with a zero block (doScatter.main starts from zeros; a rank that skipped the collective would hang the others)
+    lo1, cnt1 = rank_range(1, rank, world)
+    one = torch.zeros(n, dtype=torch.int64)
+    one[_lib.HIST_TOTAL] += cnt1                     # electrons_done of this rank's share
+    allreduce_stats(one)
+    assert int(one[_lib.HIST_TOTAL]) == 1
     q.put((rank, mine.numpy(), local.numpy(), lo, cnt))
     dist.destroy_process_group()
 

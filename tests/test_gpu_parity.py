@@ -767,3 +767,41 @@ def test_elastic_models_hot_path_cells_and_statistics(elastic):
     assert abs(eta_v - eta_g) > 3 * math.sqrt(eta_g * (1 - eta_g) * 2. / n_gpu), (eta_v, eta_g)
     van.close()
     eng.close()
+
+
+@pytest.mark.parametrize('scat', [[], ['type', 'energy']])
+def test_accumulated_pipeline_statistics_equal_one_run(scat):
+    """run_batches(accumulate=True) + pipeline_stats(): the histogram||counter block of a run split into pipelined
+    batches over several contexts (statistics accumulated on the device and merged by mcd_stats_merge; per-batch blocks
+    summed by the host when scats rows are recorded) is the block of one single run over the same ids -- what the
+    multi-GPU path all-reduces ONCE.  Also: histograms come from the pass over the els rows (hist_kernel), so they must
+    agree with a host histogram of the drained rows."""
+    from mcdiscrete_b200.probTables import genTables
+    from mcdiscrete_b200 import _lib
+    ip = base_input(scatter_output=scat, Emin=10000.)
+    eng = make_engine(scatter_output=scat, Emin=10000.)
+    genTables(ip, engine=eng)
+    N = 70000
+    eng.reset_stats()
+    whole = eng.run(count=N, first_id=300)
+    one = eng.stats_host().copy()
+    assert one[_lib.HIST_TOTAL] == N
+    h = eng.histograms()
+    bks = whole.outcome == 1
+    hist_E, _ = np.histogram(whole.els['final_E'][bks], bins=h['energy'][1])
+    assert h['energy'][0].sum() == bks.sum() and np.abs(hist_E - h['energy'][0]).sum() <= 2e-3 * bks.sum()
+    eng.reset_pipeline_stats()
+    n_b = 0
+    for r in eng.run_batches(N, 9000, first_id=300, accumulate=True, els=False):
+        n_b += 1
+        assert r.els is None
+    tot = eng.pipeline_stats(device=False)
+    assert n_b == 8 and np.array_equal(tot, one)
+    # twice the same job accumulates (no reset in between), and the device tensor is the context's own block
+    if not scat:
+        for _ in eng.run_batches(N, 9000, first_id=300, accumulate=True, els=False):
+            pass
+        t = eng.pipeline_stats()
+        assert t.data_ptr() == eng.stats_tensor().data_ptr()
+        assert np.array_equal(t.cpu().numpy(), 2 * one)
+    eng.close()
