@@ -142,8 +142,15 @@ int order_is_static(const mcd_params& p, const mcd_material& mt, const int* orde
     s[1] = quinn_sigma_host(E, mt.plasmon_e, mt.fermi_e, mt.atnd);
     s[2] = moller_sigma_host(E, p.Wc, mt.n_val);
     for (int k = 0; k < mt.n_shells; ++k) s[3 + k] = gryz_sigma_host(E, mt.shell_E[order[k]], mt.shell_n[order[k]]);
-    for (int k = 1; k < mt.n_shells + 3; ++k)
-      if (!(s[k - 1] > 1.001 * s[k]) || s[k] <= 0.0) return 0;
+    // A shell whose binding energy lies above E has sigma = 0 (crossSections.py:235-236); zeros must be TRAILING (the
+    // stable descending sort of pickFromSigmas leaves them last, and a zero-width interval is never picked), every
+    // positive value must exceed its successor by the margin.
+    bool zeros = false;
+    for (int k = 1; k < mt.n_shells + 3; ++k) {
+      if (s[k] < 0.0) return 0;
+      if (s[k] == 0.0) { zeros = true; continue; }
+      if (zeros || !(s[k - 1] > 1.001 * s[k])) return 0;
+    }
   }
   return 1;
 }

@@ -562,6 +562,8 @@ def test_pipelined_batches_equal_single_run():
     (dict(Emin=10000.), 37),                                     # less than two warps of work
     (dict(material='Cu', Emin=10000.), 30000),                   # S = 4
     (dict(material='Au', E0=30000., Emin=15000., s_tilt=0., maxScatt=10000), 12000),     # S = 8, long trajectories
+    (dict(material='Au', E0=25000., Emin=12500., maxScatt=10000), 12000),     # the 2s2p shell (12980 eV) switches off inside the range
+    (dict(material='Cu', E0=15000., Emin=7500., maxScatt=10000), 20000),      # the 1s shell (8980 eV) likewise
     (dict(Emin=10000., maxScatt=40), 20000),                     # mostly 'long' outcomes
     (dict(s_tilt=89.5, Emin=19985.), 20000),                     # bks -> abs double records (Q4)
     (dict(Emin=10000., thickness=2000.), 20000),                 # thin film: transmission
@@ -664,7 +666,10 @@ def test_device_regrouping_of_scats_rows():
 
 
 @pytest.mark.parametrize('name,E0,Emin', [('Si', 20000., 10000.), ('Cu', 20000., 10000.), ('Au', 30000., 15000.),
-                                          ('Al', 30000., 2600.)])
+                                          ('Al', 30000., 2600.),
+                                          # a core shell's binding energy inside / above [Emin, E0]: its sigma is 0 below
+                                          # it (trailing zeros in the descending order, C5 cells)
+                                          ('Au', 25000., 12500.), ('Cu', 15000., 7500.), ('Cu', 5000., 2500.)])
 def test_cumulative_cross_sections_of_the_hot_path(name, E0, Emin):
     """The cumulative inverse mean free paths the trajectory kernel uses (built and verified at mcd_create) against
     the float64 formulas.  The total (it sets the path length) and the table-channel boundaries are per-cell
