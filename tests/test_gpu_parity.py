@@ -687,7 +687,9 @@ def test_cumulative_cross_sections_of_the_hot_path(name, E0, Emin):
     rel = np.abs(cum - ref) / ref[:, -1:]
     assert rel[:, 2:].max() < 3e-7
     assert rel[:, :2].max() < 2e-6
-    assert (np.diff(cum, axis=1) >= 0).all()
+    # (a shell whose sigma is 0 at E adds nothing: its boundary equals the one before it up to the fit error, and a
+    # pick that close to a boundary takes the exact path)
+    assert (np.diff(cum, axis=1) >= -3e-7 * cum[:, -1:]).all()
     eng.close()
 
 
