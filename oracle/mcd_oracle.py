@@ -16,6 +16,7 @@ Units follow the reference: eV, Angstrom, cm^2, m^-3.
 """
 import bisect
 import math
+import os
 
 import numpy as np
 
@@ -156,9 +157,64 @@ def mfp_from_sigma(sigma, n):
     return 1. / (n * sigma) * 1e14
 
 
-def sigmas_ds(E, mat, Wc, elastic='Ruth_vanilla'):
-    """scattering.py:485-508: list in insertion order Ruth, Moller, Gryz<shell>..., Quinn."""
-    s = [elastic_sigma(E, mat.Z, elastic, 'DS'), moller_sigma(E, Wc, mat.n_val)]
+class MottTable:
+    """extFunctions.py:21-109: numerical elastic cross-sections in the ioffe.ru/ES/Elastic layout.
+    ``Es`` ascending (the file is descending and is flipped, :93-97), ``sigmas[i]`` in cm^2, ``probTable[i][j]`` =
+    cumulative SUM of dCS over the angle grid divided by the row sum (no solid-angle weight, :99-109)."""
+
+    def __init__(self, Z, name, path='../tables/mott/'):
+        self.Z, self.name = Z, name
+        self.ioffeFile = os.path.join(path + 'ioffe/' + name + '.ioffe')                  # :47
+        with open(self.ioffeFile, 'r') as f:
+            lines = f.readlines()
+        if int(lines[2].split()[-1]) != Z:                                                  # :58-60
+            raise ValueError('Trying to read file %s but expecting Z:%s' % (self.ioffeFile, Z))
+        self.sizeTheta = int(lines[5].split()[0])                                           # :62
+        self.sizeE = int(lines[6].split()[0])                                               # :63
+        self.Es = np.empty(self.sizeE)
+        self.sigmas = np.empty(self.sizeE)
+        self.dCS = np.empty([self.sizeE, self.sizeTheta])
+        self.thetas = None
+        self.probTable = None
+
+    def read_ioffe(self):                                                                   # :75-97
+        with open(self.ioffeFile, 'r') as f:
+            lines = f.readlines()
+        self.thetas = np.array([float(x) for x in lines[12].strip('theta [grad]=').split()])
+        for i, line in enumerate(lines[14:-1]):
+            items = line.replace('|', '').split()
+            self.Es[i] = float(items[0])
+            self.sigmas[i] = float(items[-1])
+            self.dCS[i] = np.array([float(x) for x in items[1:-1]])
+        self.Es = np.flip(self.Es)
+        self.sigmas = np.flip(self.sigmas)
+        self.dCS = np.flip(self.dCS, axis=0)
+        return self
+
+    def to_prob_table(self):                                                                # :99-109
+        cum = np.cumsum(self.dCS, axis=1)
+        self.probTable = cum / np.broadcast_to(np.sum(self.dCS, axis=1), cum.T.shape).T
+        return self
+
+
+def mott_sigma(tab, E):
+    """scattering.py:493: sigmas[bisect_left(Es, E)] (cm^2)."""
+    return float(tab.sigmas[bisect.bisect_left(tab.Es, E)])
+
+
+def pick_mott_table(tab, E, u):
+    """scattering.py:96-122: row bisect_left(Es, E), column bisect_left(CDF row, u), cos^2(radians(theta/2)).
+    Returns (c2, iE, jT)."""
+    iE = bisect.bisect_left(tab.Es, E)
+    jT = bisect.bisect_left(tab.probTable[iE], u)
+    theta = tab.thetas[jT]
+    return float(np.cos(np.radians(theta * 0.5)) ** 2), iE, jT
+
+
+def sigmas_ds(E, mat, Wc, elastic='Ruth_vanilla', mott=None):
+    """scattering.py:485-508: list in insertion order Ruth (or Mott, :493), Moller, Gryz<shell>..., Quinn."""
+    s = [mott_sigma(mott, E) if elastic == 'Mott' else elastic_sigma(E, mat.Z, elastic, 'DS'),
+         moller_sigma(E, Wc, mat.n_val)]
     s += [gryz_sigma(E, mat.Es[i], mat.ns[i]) for i in range(len(mat.Es))]
     s.append(quinn_sigma(E, mat.plasmon_e, mat.fermi_e, mat.atnd))
     return s
@@ -456,6 +512,8 @@ def gen_tables(inputPar, mat=None, strict=True, gryz='outermost'):
         shells = shells[:1]
     t['Gryz'] = [ProbTable('Gryzinski', mat, Erange, inputPar['tol_E'], inputPar['tol_W'],
                            shell=s).set_axes(strict).generate() for s in shells]
+    if 'Mott' in inputPar.get('elastic', ''):                              # probTables.py:601-613
+        t['Mott'] = MottTable(mat.Z, mat.species, inputPar.get('mott_path', '../tables/mott/')).read_ioffe().to_prob_table()
     return t
 
 
@@ -555,17 +613,21 @@ def ds_event(el, mat, Wc, thickness, tables, us, gryz_per_shell=False, elastic='
     (singleScatter.py:25-41 + scattering.py:530-679).  ``us`` = (u_type, u_path, u_channel, u_phi);
     u_channel is unused for Quinn.  Returns the scats row."""
     E = el.energy
-    sig = sigmas_ds(E, mat, Wc, elastic)
+    mott = tables.get('Mott') if elastic == 'Mott' else None
+    sig = sigmas_ds(E, mat, Wc, elastic, mott)
     mfp = mfp_from_sigma(sum(sig), mat.atnd)                               # scattering.py:519
     row = {'position': el.xyz.copy(), 'E': E}
     ch = pick_from_sigmas(sig, us[0])                                      # :530-549
-    row['type'] = mat.channel_names[ch]
+    row['type'] = 'Mott' if (ch == 0 and elastic == 'Mott') else mat.channel_names[ch]
     row['channel'] = ch
     pathl = -mfp * math.log(us[1])                                         # :551-565
     row['pathl'] = pathl
     el.update_xyz(pathl, thickness)
     nsh = len(mat.Es)
-    if ch == 0:                                                            # Ruth :575-577
+    if ch == 0 and elastic == 'Mott':                                      # Mott :588-591
+        W = 0.
+        c2, _, _ = pick_mott_table(mott, E, us[2])
+    elif ch == 0:                                                          # Ruth :575-577
         W = 0.
         c2 = rutherford_halfpol(E, mat.Z, us[2])
     elif ch == 1:                                                          # Moller :602-609

@@ -251,6 +251,45 @@ def test_trajectories_DS_thin_film_and_Au():
     assert len(np.unique(g['type'])) >= 8                                           # most of the 11 channels occur
 
 
+# ---- elastic = 'Mott' (extFunctions.py:21-153, scattering.py:96-122, :493, :588-591) on the synthetic ioffe-layout
+# fixture tests/data/tables/mott/ioffe/Si.ioffe; goldens by the reference's own classes (oracle/gen_golden_mott.py) ----
+MOTT_PATH = os.path.join(os.path.dirname(__file__), 'data', 'tables', 'mott') + os.sep
+
+
+def _mott_oracle():
+    return o.MottTable(14, 'Si', MOTT_PATH).read_ioffe().to_prob_table()
+
+
+def test_mott_table_parse_cdf_and_picks():
+    g = load('mott_Si.npz')
+    t = _mott_oracle()
+    for k in ('Es', 'sigmas', 'thetas', 'dCS', 'probTable'):
+        assert np.array_equal(getattr(t, k), g[k]), k                      # bit-exact: same numpy operations
+    assert (np.diff(t.Es) > 0).all() and t.probTable.shape == (56, 101)
+    c2 = [o.pick_mott_table(t, float(E), float(u))[0] for E, u in zip(g['pick_E'], g['pick_u'])]
+    assert np.array_equal(np.array(c2), g['pick_c2'])
+    sg = [o.mott_sigma(t, float(E)) for E in g['pick_E']]
+    assert np.array_equal(np.array(sg), g['pick_sigma'])
+    # what the reference does with Mott in continuous mode is recorded, not assumed (the product refuses it)
+    assert 'tableMott' in str(g['cont_behaviour'])
+    with pytest.raises(ValueError):
+        o.MottTable(13, 'Si', MOTT_PATH)                                     # Z check, extFunctions.py:58-60
+
+
+def test_trajectories_DS_mott():
+    g = load('traj_DS_Si_mott.npz')
+    ip = dict(E0=20000., Emin=15000., material='Si', s_tilt=70., thickness=3e6, mode='DS', maxScatt=1000, Wc=10.,
+              elastic='Mott')
+    mat = o.Material('Si')
+    tabs = _tables_from_golden('Si_15k_small', mat)
+    tabs['Mott'] = _mott_oracle()
+    ids = g['ids']
+    els = o.run_electrons(ip, int(ids[0]), len(ids), 12345, tabs, mat)
+    _check_traj(g, els, ['type', 'position', 'pathl', 'E', 'E_loss', 'pol_angle', 'az_angle', 'energy', 'direction'])
+    assert int(g['n_mott']) > 500 and els[0].scats[0]['type'] in ('Mott', 'Moller', 'Quinn', 'Gryz1s', 'Gryz2s', 'Gryz2p')
+    assert sum(r['type'] == 'Mott' for e in els for r in e.scats) == int(g['n_mott'])
+
+
 def test_philox_known_answer():
     """Random123 known-answer vectors for Philox4x32-10."""
     assert o.philox4x32_10((0, 0, 0, 0), (0, 0)) == (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)
