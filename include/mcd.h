@@ -56,7 +56,11 @@ enum { MCD_BETHE_CLASSICAL = 0, MCD_BETHE_JL = 1, MCD_BETHE_EXPLICIT = 2 };
  * (mcdiscrete_b200/engine.py::elastic_kind).  The polar angle is Rutherford_halfPol with the vanilla screening
  * parameter for every model (scattering.py:575-577, :829). */
 enum { MCD_ELASTIC_RUTH_VANILLA = 0, MCD_ELASTIC_RUTH_VANILLA_WDEFL = 1, MCD_ELASTIC_RUTH_NIGRAM = 2,
-       MCD_ELASTIC_RUTH_NIGRAM_WDEFL = 3 };
+       MCD_ELASTIC_RUTH_NIGRAM_WDEFL = 3,
+       /* elastic = 'Mott' (DS mode only; the reference's continuous classes crash on it): the elastic channel is
+        * labelled 'Mott', its cross-section is a step function of E read from the table (scattering.py:493) and
+        * its polar angle comes from pickMottTable (scattering.py:96-122, :588-591).  Needs mcd_mott_upload. */
+       MCD_ELASTIC_MOTT = 4 };
 /* tables['Gryz'][0] is read for EVERY shell in the reference (scattering.py:625) */
 enum { MCD_GRYZ_OUTERMOST = 0, MCD_GRYZ_PER_SHELL = 1 };
 /* table slots: 0 = Moller, 1 + k = Gryzinski table k in the reference's tables['Gryz'] order
@@ -176,6 +180,13 @@ int mcd_table_build(mcd_ctx* ctx, int slot, const float* Es, uint32_t nE, const 
  * cdf is nE x (nW-1) float32 row-major, zeros = masked. */
 int mcd_table_upload(mcd_ctx* ctx, int slot, const float* Es, uint32_t nE, const float* Ws, uint32_t nW,
                      const float* cdf);
+/* The Mott table of `elastic = Mott` (mottTable, extFunctions.py:21-153, as genTables builds it,
+ * probTables.py:601-613): Es[nE] ascending in eV, sigmas[nE] in cm^2, cdf = probTable nE x nT row-major (cumulative
+ * sums over the angle grid divided by the row sum, float64 like the reference keeps it), thetas[nT] in degrees.
+ * Replaces: tables['Mott'] read at scattering.py:466-467, :493 and :591.  E0 must not exceed Es[nE-1] (the
+ * reference raises IndexError there).  Only valid on a context created with MCD_ELASTIC_MOTT. */
+int mcd_mott_upload(mcd_ctx* ctx, uint32_t nE, uint32_t nT, const double* Es, const double* sigmas, const double* cdf,
+                    const double* thetas);
 int mcd_table_shape(const mcd_ctx* ctx, int slot, uint32_t* nE, uint32_t* nW);
 int mcd_table_download(mcd_ctx* ctx, int slot, float* cdf_out);   /* nE x (nW-1) float32 */
 
@@ -266,6 +277,10 @@ int mcd_test_rotate(mcd_ctx* ctx, const float* d_in, const float* y_in, const fl
 int mcd_test_stopping(mcd_ctx* ctx, int bethe, const float* E, uint64_t n, float* sp_out);
 int mcd_test_lookup(mcd_ctx* ctx, int slot, const float* E, const float* u, uint64_t n, float* W_out,
                     int32_t* iE_out, int32_t* jW_out);
+/* Mott hooks: sigma_out = sigmas[bisect_left(Es, E)] in cm^2 (scattering.py:493); c2_out = pickMottTable(E) with
+ * the injected uniform u (scattering.py:96-122), iE_out / jT_out = the two bisect_left results. */
+int mcd_test_mott(mcd_ctx* ctx, const float* E, const float* u, uint64_t n, float* sigma_out, float* c2_out,
+                  int32_t* iE_out, int32_t* jT_out);
 /* One loop iteration (after the maxScatt check).  state = [E, x,y,z, dx,dy,dz, yx,yy,yz] (n x 10);
  * u = n x 4 (DS: type,path,channel,phi; cont: path,polar,phi,unused);
  * row_out = n x 8: [channel, pathl, E_loss, c2, halfPhi, energy_after, outcome(-1 none), flags]. */

@@ -72,6 +72,7 @@ SYMBOLS = {
     'mcd_clone': (C.c_int, [_P, C.POINTER(_P)]),
     'mcd_table_build': (C.c_int, [_P, C.c_int, _F, C.c_uint32, _F, C.c_uint32, C.c_double, C.c_double, _P]),
     'mcd_table_upload': (C.c_int, [_P, C.c_int, _F, C.c_uint32, _F, C.c_uint32, _F]),
+    'mcd_mott_upload': (C.c_int, [_P, C.c_uint32, C.c_uint32] + [C.POINTER(C.c_double)] * 4),
     'mcd_table_shape': (C.c_int, [_P, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     'mcd_table_download': (C.c_int, [_P, C.c_int, _F]),
     'mcd_set_capacity': (C.c_int, [_P, _U64, _U64]),
@@ -106,6 +107,7 @@ SYMBOLS = {
     'mcd_test_rotate': (C.c_int, [_P, _F, _F, _F, _F, _F, _U64, _F, _F]),
     'mcd_test_stopping': (C.c_int, [_P, C.c_int, _F, _U64, _F]),
     'mcd_test_lookup': (C.c_int, [_P, C.c_int, _F, _F, _U64, _F, _I, _I]),
+    'mcd_test_mott': (C.c_int, [_P, _F, _F, _U64, _F, _F, _I, _I]),
     'mcd_test_step': (C.c_int, [_P, _F, _F, _U64, _F, _F]),
     'mcd_test_philox': (C.c_int, [_U64, _U64, C.c_uint32, C.POINTER(C.c_uint32), _F]),
 }

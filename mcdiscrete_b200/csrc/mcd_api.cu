@@ -42,6 +42,7 @@ struct mcd_ctx {
   size_t l2_persist_bytes = 0;                // persisting-L2 carve-out (0 = not used)
   float4* sig_poly = nullptr;                 // per-cell quadratics of the cumulative cross-sections
   double sig_poly_err = 0.0;                  // verified max error relative to the total
+  float* mott_dev[4] = {nullptr, nullptr, nullptr, nullptr};   // Mott table: Es, s, cdf, om (elastic = Mott)
   float4* sig_hot = nullptr;                  // hot records (Ruth / Ruth+Quinn boundaries, total) on a finer grid
   double sig_hot_err = 0.0;                   // verified max error of the two linear boundaries
   int slot_order[MCD_MAX_SHELLS] = {0};
@@ -398,7 +399,9 @@ void build_dev_params(mcd_ctx* c) {
     P.pkey[2 * r] = P.seed_lo + (uint32_t)r * 0x9E3779B9u;
     P.pkey[2 * r + 1] = P.seed_hi + (uint32_t)r * 0xBB67AE85u;
   }
-  P.order_static = (p.mode == MCD_MODE_DS) ? order_is_static(p, mt, order) : 0;
+  // (elastic = Mott: the elastic cross-section is a step function of E that arrives with mcd_mott_upload; the
+  // kernel checks the order per event and evaluates the channels directly, no per-cell records)
+  P.order_static = (p.mode == MCD_MODE_DS && p.elastic != MCD_ELASTIC_MOTT) ? order_is_static(p, mt, order) : 0;
   memcpy(c->slot_order, order, sizeof(int) * MCD_MAX_SHELLS);
   P.scat_mask = p.scat_mask;
   P.flags = p.flags;
@@ -562,8 +565,11 @@ int mcd_create(const mcd_params* p, const mcd_material* m, int device, mcd_ctx**
     return fail(nullptr, MCD_ERR_INVALID, "n_shells=%d outside 1..%d", m->n_shells, MCD_MAX_SHELLS);
   if (p->mode != MCD_MODE_DS && p->mode != MCD_MODE_CONT) return fail(nullptr, MCD_ERR_INVALID, "bad mode %d", p->mode);
   if (p->bethe < 0 || p->bethe > 2) return fail(nullptr, MCD_ERR_INVALID, "bad Bethe model %d", p->bethe);
-  if (p->elastic < MCD_ELASTIC_RUTH_VANILLA || p->elastic > MCD_ELASTIC_RUTH_NIGRAM_WDEFL)
-    return fail(nullptr, MCD_ERR_INVALID, "bad elastic model %d (Mott / Browning are not on the path)", p->elastic);
+  if (p->elastic < MCD_ELASTIC_RUTH_VANILLA || p->elastic > MCD_ELASTIC_MOTT)
+    return fail(nullptr, MCD_ERR_INVALID, "bad elastic model %d (Browning is not on the path)", p->elastic);
+  if (p->elastic == MCD_ELASTIC_MOTT && p->mode != MCD_MODE_DS)
+    return fail(nullptr, MCD_ERR_INVALID, "elastic = Mott exists in DS mode only (the reference's continuous classes "
+                "never receive the table: scattering.py:794 raises AttributeError)");
   if (!(p->E0 > p->Emin) || !(p->Emin > 0)) return fail(nullptr, MCD_ERR_INVALID, "need E0 > Emin > 0");
   if (p->mode == MCD_MODE_DS && !(p->Emin > m->plasmon_e))
     return fail(nullptr, MCD_ERR_INVALID, "DS needs Emin > plasmon energy (quinn_sigma, crossSections.py:272-281)");
@@ -655,7 +661,7 @@ int mcd_destroy(mcd_ctx* c) {
   if (!c) return MCD_OK;
   cudaSetDevice(c->device);
   if (c->owns_tables) for (auto& t : c->tab) free_table(t);
-  if (c->owns_tables) { cudaFree(c->sig_poly); cudaFree(c->sig_hot); }
+  if (c->owns_tables) { cudaFree(c->sig_poly); cudaFree(c->sig_hot); for (float* q : c->mott_dev) cudaFree(q); }
   cudaFree(c->els); cudaFree(c->scats); cudaFree(c->chunk_next); cudaFree(c->chunk_count); cudaFree(c->ticket);
   cudaFree(c->rq[0]); cudaFree(c->rq[1]);
   cudaFree(c->nev); cudaFree(c->sorted); cudaFree(c->offsets); cudaFree(c->tile_tmp); cudaFree(c->total_dev);
@@ -706,6 +712,55 @@ int mcd_table_upload(mcd_ctx* c, int slot, const float* Es, uint32_t nE, const f
   CU(c, mcd_launch_table_nvalid(h.cdf, (int)nE, (int)nW, h.nvalid, 0));
   CU(c, mcd_launch_table_guide(h.cdf, (int)nE, (int)nW, h.nvalid, h.guide, 0));
   CU(c, cudaDeviceSynchronize());
+  return MCD_OK;
+}
+
+// largest float32 that is <= x: for a float32 v, (x < v) == (round_down(x) < v)
+static float f32_round_down(double x) {
+  float f = (float)x;
+  if ((double)f > x) f = nextafterf(f, -INFINITY);
+  return f;
+}
+
+int mcd_mott_upload(mcd_ctx* c, uint32_t nE, uint32_t nT, const double* Es, const double* sigmas, const double* cdf,
+                    const double* thetas) {
+  int rc = need_ctx(c);
+  if (rc) return rc;
+  if (c->par.elastic != MCD_ELASTIC_MOTT) return fail(c, MCD_ERR_STATE, "the context was not created with elastic = Mott");
+  if (!c->owns_tables) return fail(c, MCD_ERR_STATE, "tables of a cloned context belong to its parent");
+  if (!Es || !sigmas || !cdf || !thetas || nE < 2 || nT < 2) return fail(c, MCD_ERR_INVALID, "Mott table: null or too small");
+  for (uint32_t i = 0; i < nE; ++i) {
+    if (i && !(Es[i] > Es[i - 1])) return fail(c, MCD_ERR_INVALID, "Mott table: Es not strictly increasing at %u", i);
+    if (!(sigmas[i] > 0.0)) return fail(c, MCD_ERR_INVALID, "Mott table: sigma[%u] is not positive", i);
+  }
+  // bisect_left(Es, E) == nE raises IndexError in the reference (scattering.py:493)
+  if (c->par.E0 > Es[nE - 1])
+    return fail(c, MCD_ERR_INVALID, "Mott table ends at %g eV but E0 = %g eV", Es[nE - 1], c->par.E0);
+  std::vector<float> hEs(nE), hs(nE), hcdf((size_t)nE * nT), hom(nT);
+  const double scale = c->mat.atnd * 1e-14;                           // scattering.py:35
+  for (uint32_t i = 0; i < nE; ++i) {
+    hEs[i] = f32_round_down(Es[i]);
+    hs[i] = (float)(sigmas[i] * scale);
+    for (uint32_t j = 0; j < nT; ++j) {
+      const double v = cdf[(size_t)i * nT + j];
+      if (j && v < cdf[(size_t)i * nT + j - 1]) return fail(c, MCD_ERR_INVALID, "Mott table: CDF row %u decreases at %u", i, j);
+      hcdf[(size_t)i * nT + j] = f32_round_down(v);
+    }
+  }
+  for (uint32_t j = 0; j < nT; ++j) {
+    const double ch = cos(thetas[j] * 0.5 * M_PI / 180.0);              // scattering.py:122: cos(radians(theta/2))^2
+    hom[j] = (float)(1.0 - ch * ch);
+  }
+  for (float*& q : c->mott_dev) { cudaFree(q); q = nullptr; }
+  const size_t sz[4] = {nE * sizeof(float), nE * sizeof(float), (size_t)nE * nT * sizeof(float), nT * sizeof(float)};
+  const float* src[4] = {hEs.data(), hs.data(), hcdf.data(), hom.data()};
+  for (int k = 0; k < 4; ++k) {
+    CU(c, cudaMalloc(&c->mott_dev[k], sz[k]));
+    CU(c, cudaMemcpy(c->mott_dev[k], src[k], sz[k], cudaMemcpyHostToDevice));
+  }
+  DevMott& M = c->P.mott;
+  M.Es = c->mott_dev[0]; M.s = c->mott_dev[1]; M.cdf = c->mott_dev[2]; M.om = c->mott_dev[3];
+  M.nE = (int)nE; M.nT = (int)nT;
   return MCD_OK;
 }
 
@@ -781,6 +836,8 @@ int mcd_run(mcd_ctx* c, uint64_t first_id, uint64_t count, void* stream) {
     if (c->P.gryz_per_shell)
       for (int k = 0; k < c->mat.n_shells; ++k)
         if (!c->tab[MCD_TABLE_GRYZ0 + k].cdf) return fail(c, MCD_ERR_STATE, "per-shell mode: Gryzinski table %d missing", k);
+    if (c->par.elastic == MCD_ELASTIC_MOTT && !c->P.mott.nE)
+      return fail(c, MCD_ERR_STATE, "elastic = Mott needs the Mott table (mcd_mott_upload)");
   }
   cudaStream_t s = (cudaStream_t)stream;
   CU(c, cudaMemsetAsync(c->ticket, 0, 8 * sizeof(unsigned long long), s));
@@ -1216,6 +1273,19 @@ int mcd_test_lookup(mcd_ctx* c, int slot, const float* E, const float* u, uint64
   CU(c, dE.up(E, n)); CU(c, dU.up(u, n)); CU(c, dW.alloc(n)); CU(c, dI.alloc(n)); CU(c, dJ.alloc(n));
   CU(c, mcd_launch_test_lookup(c->P, slot, dE.p, dU.p, n, dW.p, dI.p, dJ.p, 0));
   CU(c, dW.down(W_out, n)); CU(c, dI.down(iE_out, n)); CU(c, dJ.down(jW_out, n));
+  return MCD_OK;
+}
+
+int mcd_test_mott(mcd_ctx* c, const float* E, const float* u, uint64_t n, float* sigma_out, float* c2_out,
+                  int32_t* iE_out, int32_t* jT_out) {
+  int rc = need_ctx(c);
+  if (rc) return rc;
+  if (!c->P.mott.nE) return fail(c, MCD_ERR_STATE, "no Mott table (mcd_mott_upload)");
+  Tmp<float> dE, dU, dS, dC;
+  Tmp<int> dI, dJ;
+  CU(c, dE.up(E, n)); CU(c, dU.up(u, n)); CU(c, dS.alloc(n)); CU(c, dC.alloc(n)); CU(c, dI.alloc(n)); CU(c, dJ.alloc(n));
+  CU(c, mcd_launch_test_mott(c->P, dE.p, dU.p, n, dS.p, dC.p, dI.p, dJ.p, 0));
+  CU(c, dS.down(sigma_out, n)); CU(c, dC.down(c2_out, n)); CU(c, dI.down(iE_out, n)); CU(c, dJ.down(jT_out, n));
   return MCD_OK;
 }
 

@@ -60,6 +60,8 @@ cudaError_t mcd_launch_test_stopping(const DevParams& P, int bethe, const float*
                                      cudaStream_t s);
 cudaError_t mcd_launch_test_lookup(const DevParams& P, int slot, const float* E, const float* u, uint64_t n,
                                    float* W, int* iE, int* jW, cudaStream_t s);
+cudaError_t mcd_launch_test_mott(const DevParams& P, const float* E, const float* u, uint64_t n, float* sig, float* c2,
+                                 int* iE, int* jT, cudaStream_t s);
 cudaError_t mcd_launch_test_step(const DevParams& P, const float* st, const float* u, uint64_t n, float* st_out,
                                  float* row_out, cudaStream_t s);
 cudaError_t mcd_launch_test_philox(uint64_t seed, uint64_t el, uint32_t ev, uint32_t* raw, float* u,

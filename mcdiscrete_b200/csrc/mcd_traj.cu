@@ -153,7 +153,9 @@ __global__ void stats_merge_kernel(unsigned long long* __restrict__ dst, unsigne
   }
 }
 
-template <int S, int MODE, bool SCATS>
+// POLY = 1: the per-cell cross-section records exist (DevParams::use_sig_poly): no formula code, no flag tests;
+// POLY = 0: the S+3 formulas are evaluated every event (channel order not static on [Emin, E0], or elastic = Mott)
+template <int S, int MODE, bool SCATS, int POLY>
 __global__ void __launch_bounds__(kThreads, MCD_MIN_BLOCKS)
 traj_kernel(const __grid_constant__ DevParams P, const DevOut O, const unsigned long long first_id,
             const unsigned long long count) {
@@ -212,12 +214,12 @@ traj_kernel(const __grid_constant__ DevParams P, const DevOut O, const unsigned 
     row.E = e.E;
     if (has_row) {
       HotRec hr;
-      if (MODE == MCD_MODE_DS) hr = ds_hot_fetch(P, e.E);          // loads first, Philox hides their latency
+      if (MODE == MCD_MODE_DS) hr = ds_hot_fetch<POLY>(P, e.E);    // loads first, Philox hides their latency
       const float4 u = event_uniforms(P, first_id + rel_id, ev);
       if (MODE == MCD_MODE_DS) {
         EventMid mid;
         float tot;
-        ds_phase_a<S>(P, e, u, row, mid, tot, hr);
+        ds_phase_a<S, POLY>(P, e, u, row, mid, tot, hr);
         ds_phase_b<S>(P, e, u, row, mid, tot);
       } else {
         cont_event(P, e, u, row);
@@ -596,20 +598,25 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
 
 typedef void (*TrajKernel)(const DevParams, const DevOut, const unsigned long long, const unsigned long long);
 
-template <bool SCATS>
-TrajKernel pick_kernel_t(const DevParams& P) {
-  if (P.mode == MCD_MODE_CONT) return traj_kernel<1, MCD_MODE_CONT, SCATS>;
+template <bool SCATS, int POLY>
+TrajKernel pick_kernel_tp(const DevParams& P) {
   switch (P.m.nshell) {
-    case 1: return traj_kernel<1, MCD_MODE_DS, SCATS>;
-    case 2: return traj_kernel<2, MCD_MODE_DS, SCATS>;
-    case 3: return traj_kernel<3, MCD_MODE_DS, SCATS>;
-    case 4: return traj_kernel<4, MCD_MODE_DS, SCATS>;
-    case 5: return traj_kernel<5, MCD_MODE_DS, SCATS>;
-    case 6: return traj_kernel<6, MCD_MODE_DS, SCATS>;
-    case 7: return traj_kernel<7, MCD_MODE_DS, SCATS>;
-    case 8: return traj_kernel<8, MCD_MODE_DS, SCATS>;
+    case 1: return traj_kernel<1, MCD_MODE_DS, SCATS, POLY>;
+    case 2: return traj_kernel<2, MCD_MODE_DS, SCATS, POLY>;
+    case 3: return traj_kernel<3, MCD_MODE_DS, SCATS, POLY>;
+    case 4: return traj_kernel<4, MCD_MODE_DS, SCATS, POLY>;
+    case 5: return traj_kernel<5, MCD_MODE_DS, SCATS, POLY>;
+    case 6: return traj_kernel<6, MCD_MODE_DS, SCATS, POLY>;
+    case 7: return traj_kernel<7, MCD_MODE_DS, SCATS, POLY>;
+    case 8: return traj_kernel<8, MCD_MODE_DS, SCATS, POLY>;
     default: return nullptr;
   }
+}
+
+template <bool SCATS>
+TrajKernel pick_kernel_t(const DevParams& P) {
+  if (P.mode == MCD_MODE_CONT) return traj_kernel<1, MCD_MODE_CONT, SCATS, 0>;
+  return P.use_sig_poly ? pick_kernel_tp<SCATS, 1>(P) : pick_kernel_tp<SCATS, 0>(P);
 }
 
 template <bool RESUME>
@@ -761,44 +768,49 @@ __global__ void __launch_bounds__(256) scatter_rows(const uint32_t* __restrict__
 // Columnar variant: the payload words 2.. of every row go to one float column each (column j = word 2+j at byte
 // offset j * col_stride) and the channel index to a byte column; row d of every column = the event offsets[rel_id] +
 // event.  Words 0/1 (electron id, event index) are NOT stored: in trajectory order they follow from the offsets.
+//
+// One block per chunk.  The chunk (<= 1024 rows, contiguous) is staged in shared memory with coalesced loads, then
+// read back TRANSPOSED: a warp of the trajectory kernel appends the rows of one loop iteration side by side (lane
+// order) and all 32 lanes are alive until the ids run out, so rows i, i+32, i+64, ... of a chunk are consecutive
+// events of ONE electron and land in consecutive column entries.  Lane t of a warp therefore takes row t*32 + r: the
+// 32 stores of a column instruction hit one or two 128-byte lines instead of 32 different ones (the row-at-a-time
+// version wrote 2.6x its payload and read 3.2x).  Nothing depends on that structure for correctness:
+// every row still computes its own destination.  Shared-memory rows are skewed by one word per 32 rows so that the
+// transposed reads (stride 32 rows) fall on 32 different banks.
 __global__ void __launch_bounds__(256) scatter_cols(const uint32_t* __restrict__ pool,
                                                     const unsigned int* __restrict__ chunk_count, unsigned int nchunks,
                                                     int row_words, const unsigned long long* __restrict__ offsets,
                                                     unsigned char* __restrict__ cols, unsigned long long col_stride,
                                                     const unsigned int* __restrict__ nchunks_dev) {
+  extern __shared__ uint32_t s_rows[];                     // MCD_CHUNK_ROWS * row_words + 32 words
   // rows per column: a run that dropped rows (pool overflow; the caller re-runs it) has event counts beyond the
   // stored rows -- such targets are skipped instead of written past the columns
   const unsigned long long max_rows = col_stride >> 2;
   // enqueued right behind the trajectory kernel (no host round trip): the number of used chunks is still on the device
   if (nchunks_dev) nchunks = min(nchunks, *nchunks_dev);
   unsigned char* type_col = cols + (unsigned long long)(row_words - 2) * col_stride;
+  const unsigned int lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const unsigned int rw = (unsigned int)row_words;
   for (unsigned int c = blockIdx.x; c < nchunks; c += gridDim.x) {
-    const unsigned int cnt = chunk_count[c];
+    const unsigned int cnt = min(chunk_count[c], MCD_CHUNK_ROWS);
     const uint32_t* cbase = pool + (size_t)c * MCD_CHUNK_ROWS * (size_t)row_words;
-    if ((row_words & 1) == 0) {
-      const int rw2 = row_words >> 1;
-      for (unsigned int r = threadIdx.x; r < cnt; r += blockDim.x) {
-        const uint2* src = reinterpret_cast<const uint2*>(cbase) + (size_t)r * rw2;
-        const uint2 head = __ldcs(src);
-        const unsigned long long d = offsets[head.x] + (unsigned long long)(head.y & 0xffffffu);
-        if (d >= max_rows) continue;
-        type_col[d] = (unsigned char)(head.y >> 24);
-        for (int w = 1; w < rw2; ++w) {
-          const uint2 v = __ldcs(src + w);
-          reinterpret_cast<uint32_t*>(cols + (unsigned long long)(2 * w - 2) * col_stride)[d] = v.x;
-          reinterpret_cast<uint32_t*>(cols + (unsigned long long)(2 * w - 1) * col_stride)[d] = v.y;
-        }
-      }
-    } else {
-      for (unsigned int r = threadIdx.x; r < cnt; r += blockDim.x) {
-        const uint32_t* src = cbase + (size_t)r * row_words;
-        const uint32_t rel = src[0], w1 = src[1];
-        const unsigned long long d = offsets[rel] + (unsigned long long)(w1 & 0xffffffu);
-        if (d >= max_rows) continue;
-        type_col[d] = (unsigned char)(w1 >> 24);
-        for (int w = 2; w < row_words; ++w)
-          reinterpret_cast<uint32_t*>(cols + (unsigned long long)(w - 2) * col_stride)[d] = src[w];
-      }
+    const unsigned int nwords = cnt * rw;
+    __syncthreads();                                       // (the previous chunk has been consumed)
+    for (unsigned int k = threadIdx.x; k < nwords; k += 256u) {
+      const unsigned int i = k / rw;
+      s_rows[k + (i >> 5)] = __ldcs(cbase + k);
+    }
+    __syncthreads();
+    for (unsigned int r = warp; r < 32u; r += 8u) {
+      const unsigned int i = lane * 32u + r;
+      if (i >= cnt) continue;
+      const uint32_t* src = s_rows + i * rw + (i >> 5);
+      const uint32_t rel = src[0], w1 = src[1];
+      const unsigned long long d = offsets[rel] + (unsigned long long)(w1 & 0xffffffu);
+      if (d >= max_rows) continue;
+      type_col[d] = (unsigned char)(w1 >> 24);
+      for (unsigned int w = 2; w < rw; ++w)
+        reinterpret_cast<uint32_t*>(cols + (unsigned long long)(w - 2) * col_stride)[d] = src[w];
     }
   }
 }
@@ -817,10 +829,15 @@ cudaError_t mcd_launch_order_scats(const unsigned int* nev, unsigned long long c
   scan_apply<<<ntiles, kScanT, 0, stream>>>(nev, count, tile_tmp, offsets);
   if (sorted && nchunks) {
     const unsigned int grid = nchunks < (unsigned int)(sm_count * 64) ? nchunks : (unsigned int)(sm_count * 64);
-    if (col_stride)
-      scatter_cols<<<grid, 256, 0, stream>>>(pool, chunk_count, nchunks, row_words, offsets,
-                                             reinterpret_cast<unsigned char*>(sorted), col_stride, nchunks_dev);
-    else
+    if (col_stride) {
+      const size_t smem = ((size_t)MCD_CHUNK_ROWS * (size_t)row_words + 32) * sizeof(uint32_t);   // 24.1 .. 56.1 KB
+      if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(scatter_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+      }
+      scatter_cols<<<grid, 256, smem, stream>>>(pool, chunk_count, nchunks, row_words, offsets,
+                                                reinterpret_cast<unsigned char*>(sorted), col_stride, nchunks_dev);
+    } else
       scatter_rows<<<grid, 256, 0, stream>>>(pool, chunk_count, nchunks, row_words, offsets, sorted);
   }
   return cudaGetLastError();

@@ -11,7 +11,7 @@ template <int S>
 __device__ void sigmas_insertion(const DevParams& P, float E, float* out /* S+3 */, float* tot) {
   const DevMat& m = P.m;
   const float invE = f_rcp(E);
-  out[0] = s_ruth(m, E);
+  out[0] = P.mott.nE ? __ldg(P.mott.s + mott_row(P.mott, E)) : s_ruth(m, E);     // scattering.py:493
   out[1] = s_moller(m, E, invE);
   for (int k = 0; k < S; ++k) out[2 + m.gShell[k]] = s_gryz(E, invE, m.gE[k], m.gInvE[k], m.gC[k]);
   out[2 + S] = s_quinn(m, E, invE);
@@ -161,6 +161,19 @@ __global__ void k_lookup(const __grid_constant__ DevParams P, int slot, const fl
   jW[i] = b;
 }
 
+__global__ void k_mott(const __grid_constant__ DevParams P, const float* E, const float* u, uint64_t n, float* sig,
+                       float* c2, int* iE, int* jT) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int r = mott_row(P.mott, E[i]);
+  int j = 0;
+  const float om = mott_om(P.mott, r, u[i], &j);
+  sig[i] = __ldg(P.mott.s + r) * P.m.sig_scale_inv;
+  c2[i] = 1.0f - om;
+  iE[i] = r;
+  jT[i] = j;
+}
+
 template <int S>
 __device__ void step_one(const DevParams& P, bool on, ElState& e, float4 u, EventRow& row) {
   if (!on) return;
@@ -247,6 +260,8 @@ cudaError_t mcd_launch_test_lookup(const DevParams& P, int slot, const float* E,
                                    float* W, int* iE, int* jW, cudaStream_t s) {
   LAUNCH(k_lookup, n, s, P, slot, E, u, n, W, iE, jW);
 }
+cudaError_t mcd_launch_test_mott(const DevParams& P, const float* E, const float* u, uint64_t n, float* sig, float* c2,
+                                 int* iE, int* jT, cudaStream_t s) { LAUNCH(k_mott, n, s, P, E, u, n, sig, c2, iE, jT); }
 cudaError_t mcd_launch_test_step(const DevParams& P, const float* st, const float* u, uint64_t n, float* st_out,
                                  float* row_out, cudaStream_t s) { LAUNCH(k_step, n, s, P, st, u, n, st_out, row_out); }
 cudaError_t mcd_launch_test_philox(uint64_t seed, uint64_t el, uint32_t ev, uint32_t* raw, float* u,

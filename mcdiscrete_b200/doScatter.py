@@ -62,7 +62,7 @@ def main(argv=None):
         path += '.rank%d' % rank
     os.makedirs(os.path.dirname(path) or '.', exist_ok=True)
     lo, n = rank_range(int(inputPar['num_el']), rank, world)
-    names = eng.material.channel_names
+    names = eng.channel_names
     t0 = time.time()
     events = 0
     import torch

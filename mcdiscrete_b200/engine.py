@@ -173,6 +173,7 @@ class RunResult:
 
 
 ELASTIC_MODELS = ('Ruth_vanilla', 'Ruth_vanilla_wDefl', 'Ruth_nigram', 'Ruth_nigram_wDefl')
+ELASTIC_MOTT = 4          # MCD_ELASTIC_MOTT
 
 
 def elastic_kind(elastic, ds):
@@ -182,10 +183,18 @@ def elastic_kind(elastic, ds):
     ruther_N_sigma, *nigram_wDefl -> ruther_N_sigma_wDefl.  Continuous mode (scattering.py:781-789) tests the
     substrings 'vanilla', 'vanilla_wDefl', 'nigram', 'nigram_wDefl' in that order, so its _wDefl branches are
     unreachable and those labels run the plain forms (tests/golden/elastic_formulas.json records both facts).
-    Mott / Browning need unshipped data or crash."""
+    'Mott' (DS only, scattering.py:466-467, :493, :588-591) takes the elastic cross-section and the polar angle from
+    the table genTables reads (probTables.py:601-613); the reference's continuous classes never receive that table
+    (scattering.py:794 raises AttributeError, recorded in tests/golden/mott_Si.npz), so it is refused there.
+    Browning does not exist in the reference's code."""
+    if elastic == 'Mott':
+        if not ds:
+            raise NotImplementedError("elastic = 'Mott' with a continuous mode: the reference raises AttributeError "
+                                      "(scattering.py:794: the class never stores tableMott)")
+        return ELASTIC_MOTT
     if elastic not in ELASTIC_MODELS:
-        raise NotImplementedError("elastic = %r: only %s are on the path (Mott / Browning need unshipped data or "
-                                  "crash in the reference, SURVEY Q10)" % (elastic, ', '.join(ELASTIC_MODELS)))
+        raise NotImplementedError("elastic = %r: only %s and Mott are on the path"
+                                  % (elastic, ', '.join(ELASTIC_MODELS)))
     if not ds:
         elastic = 'Ruth_vanilla' if 'vanilla' in elastic else 'Ruth_nigram'
     return ELASTIC_MODELS.index(elastic)
@@ -250,6 +259,15 @@ class Engine:
         self.next_id = 0
         self._pinned = {}
 
+    @property
+    def channel_names(self):
+        """The `type` labels in sigma-dict insertion order; the elastic channel is 'Mott' for elastic = 'Mott'
+        (scattering.py:493, :589)."""
+        names = list(self.material.channel_names)
+        if self.params.elastic == ELASTIC_MOTT:
+            names[0] = 'Mott'
+        return names
+
     # ---- lifetime -----------------------------------------------------------------------------
     def clone(self):
         """A second context sharing this engine's tables (mcd_clone) with its own outputs and statistics."""
@@ -293,6 +311,15 @@ class Engine:
         Es, Ws, cdf = f32(Es), f32(Ws), f32(cdf)
         assert cdf.shape == (len(Es), len(Ws) - 1), 'cdf must be nE x (nW-1)'
         self._ck(self.lib.mcd_table_upload(self.ctx, slot, fptr(Es), len(Es), fptr(Ws), len(Ws), fptr(cdf)))
+
+    def mott_upload(self, Es, sigmas, probTable, thetas):
+        """The table of elastic = 'Mott' (mottTable of extFunctions.py: Es ascending, sigmas in cm^2, probTable
+        nE x nTheta, thetas in degrees; float64 like the reference keeps them)."""
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        Es, sigmas, probTable, thetas = f64(Es), f64(sigmas), f64(probTable), f64(thetas)
+        assert probTable.shape == (len(Es), len(thetas)) and len(sigmas) == len(Es)
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        self._ck(self.lib.mcd_mott_upload(self.ctx, len(Es), len(thetas), dp(Es), dp(sigmas), dp(probTable), dp(thetas)))
 
     def table_download(self, slot):
         nE, nW = C.c_uint32(), C.c_uint32()
@@ -644,6 +671,14 @@ class Engine:
         iE, jW = np.empty(len(E), np.int32), np.empty(len(E), np.int32)
         self._ck(self.lib.mcd_test_lookup(self.ctx, slot, fptr(E), fptr(u), len(E), fptr(W), iptr(iE), iptr(jW)))
         return W, iE, jW
+
+    def test_mott(self, E, u):
+        """(sigma in cm^2, cos^2(theta/2), iE, jTheta) of the uploaded Mott table for energies E and uniforms u."""
+        E, u = f32(E), f32(u)
+        sg, c2 = np.empty(len(E), np.float32), np.empty(len(E), np.float32)
+        iE, jT = np.empty(len(E), np.int32), np.empty(len(E), np.int32)
+        self._ck(self.lib.mcd_test_mott(self.ctx, fptr(E), fptr(u), len(E), fptr(sg), fptr(c2), iptr(iE), iptr(jT)))
+        return sg, c2, iE, jT
 
     def test_step(self, state, u):
         state, u = f32(state), f32(u)

@@ -85,7 +85,7 @@ def _compatible(eng, key):
 def _per_electron_dicts(eng, res, inputPar, thingsToSave):
     """Columnar RunResult -> the reference's list of nested dict-of-lists (multiScatter.py:112)."""
     el_cols, sc_cols = list(thingsToSave['el_output']), list(thingsToSave['scat_output'])
-    names = eng.material.channel_names
+    names = eng.channel_names
     cont = 'DS' not in inputPar['mode']
     sc = res.sorted_scats()
     n = res.count

@@ -178,7 +178,7 @@ class probTable:
 
 
 def genTables(inputPar, engine=None, gryz=None, mapTarget='../tables/integration'):
-    """probTables.py:541-614.  Returns {'Moller': probTable, 'Gryz': [probTable, ...]} with
+    """probTables.py:541-614.  Returns {'Moller': probTable, 'Gryz': [probTable, ...] (, 'Mott': mottTable)} with
     ``tables['Gryz'][0]`` = the outermost shell (reversed name_s, :579).  The rows live on the device of
     ``engine`` (created from inputPar when not given)."""
     from .engine import Engine
@@ -200,5 +200,11 @@ def genTables(inputPar, engine=None, gryz=None, mapTarget='../tables/integration
     for k, sh in enumerate(shells):
         gt = probTable('Gryzinski', sh, Erange, inputPar['tol_E'], inputPar['tol_W'], mat)
         tables['Gryz'].append(gt.generate(engine, 1 + k) if gen else gt.readFromMemory(engine, 1 + k, mapTarget))
+    if 'Mott' in inputPar.get('elastic', ''):                  # probTables.py:601-613
+        from .extFunctions import mottTable
+        mott = mottTable(mat.params['Z'], mat.species, inputPar.get('mott_path', '../tables/mott/'))
+        mott.readIoffe().toProbTable().upload(engine)
+        tables['Mott'] = mott
+        print('assigned Mott table \n')
     engine.tables = tables
     return tables

@@ -208,3 +208,41 @@ def test_multiScatter_engine_key_covers_every_parameter():
     assert _run_key(dict(c, Bethe_model='JL'), mat, tts) != _run_key(c, mat, tts)
     # continuous mode: the _wDefl labels run the plain forms (scattering.py:781-789) -> same physics, same key
     assert _run_key(dict(c, elastic='Ruth_vanilla_wDefl'), mat, tts) == _run_key(c, mat, tts)
+
+
+def test_mottTable_host_mirror_matches_the_reference(tmp_path):
+    """mcdiscrete_b200.extFunctions.mottTable / pickMottTable against the arrays and picks the reference's own
+    classes produced on the same (synthetic, ioffe-layout) file -- tests/golden/mott_Si.npz by
+    oracle/gen_golden_mott.py (extFunctions.py:21-153, scattering.py:96-122)."""
+    import random
+    import shutil
+    from mcdiscrete_b200.extFunctions import mottTable, pickMottTable
+    from mcdiscrete_b200.engine import elastic_kind, ELASTIC_MOTT
+    g = np.load(os.path.join(GOLD, 'mott_Si.npz'))
+    work = tmp_path / 'mott'
+    shutil.copytree(os.path.join(ROOT, 'tests', 'data', 'tables', 'mott'), work)
+    mt = mottTable(14, 'Si', str(work) + os.sep)
+    assert (mt.sizeE, mt.sizeTheta) == g['probTable'].shape
+    mt.readIoffe().toProbTable()
+    for k in ('Es', 'sigmas', 'thetas', 'dCS', 'probTable'):
+        assert np.array_equal(np.asarray(getattr(mt, k), float), g[k]), k
+    saved = random.random
+    try:
+        for E, u, c2 in zip(g['pick_E'], g['pick_u'], g['pick_c2']):
+            random.random = lambda u=u: float(u)
+            assert pickMottTable(mt, float(E)) == c2
+    finally:
+        random.random = saved
+    # the float32 memmap round trip (mapToMemory / readFromMemory, :112-145)
+    mt.mapToMemory()
+    m2 = mottTable(14, 'Si', str(work) + os.sep).readFromMemory()
+    assert m2.probTable.dtype == np.float32 and np.array_equal(m2.probTable, g['probTable'].astype(np.float32))
+    assert np.array_equal(m2.Es, g['Es'])
+    with pytest.raises(ValueError):
+        mottTable(13, 'Si', str(work) + os.sep)                  # Z check (:58-60)
+    with pytest.raises(FileNotFoundError):
+        mottTable(29, 'Cu', str(work) + os.sep)
+    assert elastic_kind('Mott', True) == ELASTIC_MOTT
+    with pytest.raises(NotImplementedError):
+        elastic_kind('Mott', False)                              # AttributeError in the reference (golden records it)
+    assert 'tableMott' in str(g['cont_behaviour'])

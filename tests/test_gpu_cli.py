@@ -109,7 +109,7 @@ def test_error_behaviour_and_legacy_wrappers():
     with pytest.raises(ValueError):
         Engine(dict(ip, scatter_output=['nonsense']), device=0)
     with pytest.raises(NotImplementedError):
-        Engine(dict(ip, elastic='Mott'), device=0)
+        Engine(dict(ip, elastic='Browning'), device=0)            # not a model of the reference's code
     with pytest.raises(_lib.MCDError):                            # Emin below the plasmon energy (quinn_sigma :272-281)
         Engine(dict(ip, Emin=10.), device=0)
     eng.close()

@@ -776,6 +776,117 @@ def test_elastic_models_hot_path_cells_and_statistics(elastic):
     eng.close()
 
 
+# ---- elastic = 'Mott' (extFunctions.py:21-153, scattering.py:96-122, :493, :588-591) on the synthetic
+# ioffe-layout fixture; goldens by the reference's own classes (oracle/gen_golden_mott.py) -----------------------------
+MOTT_PATH = os.path.join(os.path.dirname(__file__), 'data', 'tables', 'mott') + os.sep
+
+
+def _mott_engine(**kw):
+    from mcdiscrete_b200.extFunctions import mottTable
+    eng = make_engine(elastic='Mott', **kw)
+    upload_golden(eng, golden_tables('Si_15k_small'))
+    mt = mottTable(14, 'Si', MOTT_PATH).readIoffe().toProbTable().upload(eng)
+    return eng, mt
+
+
+def test_mott_table_lookup_bit_exact_and_sigma():
+    """sigma(E) and pickMottTable on the device: both bisect_left indices bit-exact against the float64 oracle on
+    float32 inputs (thresholds rounded down to float32 on upload), cos^2(theta/2) and sigma within 1e-6; the
+    reference's own (E, u, c2) cases included."""
+    g = np.load(os.path.join(GOLD, 'mott_Si.npz'))
+    eng, mt = _mott_engine()
+    for k in ('Es', 'sigmas', 'thetas', 'probTable'):
+        assert np.array_equal(np.asarray(getattr(mt, k), float), g[k]), k       # host mirror == reference object
+    ot = o.MottTable(14, 'Si', MOTT_PATH).read_ioffe().to_prob_table()
+    rng = np.random.default_rng(21)
+    E = np.concatenate([rng.uniform(60., 20000., 20000), g['pick_E'][g['pick_E'] <= 20000.],
+                        g['Es'][g['Es'] <= 20000.], np.nextafter(g['Es'][g['Es'] < 20000.].astype(np.float32), np.float32(3e4))])
+    E = E.astype(np.float32)
+    u = rng.uniform(0., 1., len(E))
+    k_ = min(len(u), g['probTable'].shape[1])
+    u[:k_] = g['probTable'][30, :k_]                                            # exact CDF values: bisect_left ties
+    u = np.clip(u.astype(np.float32), 1e-7, 0.9999999)
+    sg, c2, iE, jT = eng.test_mott(E, u)
+    ref = [o.pick_mott_table(ot, float(e), float(x)) for e, x in zip(E, u)]
+    assert np.array_equal(iE, [r[1] for r in ref]) and np.array_equal(jT, [r[2] for r in ref])
+    assert np.abs(c2 - np.array([r[0] for r in ref])).max() < 1e-6
+    assert relerr(sg, [o.mott_sigma(ot, float(e)) for e in E]).max() < REL
+    # the reference's own cases (float64 E and u rounded to float32 may move across a threshold: compare on the
+    # float32 values, which is what the device sees)
+    Eg, ug = g['pick_E'].astype(np.float32), np.clip(g['pick_u'].astype(np.float32), 1e-7, 0.9999999)
+    keep = Eg <= 20000.
+    sg2, c22, iE2, jT2 = eng.test_mott(Eg[keep], ug[keep])
+    ref2 = [o.pick_mott_table(ot, float(e), float(x)) for e, x in zip(Eg[keep], ug[keep])]
+    assert np.array_equal(jT2, [r[2] for r in ref2]) and np.abs(c22 - np.array([r[0] for r in ref2])).max() < 1e-6
+    # where rounding the inputs to float32 did not move them across a table threshold the reference's own answer holds
+    same_cell = np.array([o.pick_mott_table(ot, float(e), float(x))[1:] == o.pick_mott_table(ot, float(e32), float(x32))[1:]
+                          for e, x, e32, x32 in zip(g['pick_E'][keep], g['pick_u'][keep], Eg[keep], ug[keep])])
+    assert same_cell.sum() > 250 and np.abs(c22[same_cell] - g['pick_c2'][keep][same_cell]).max() < 1e-6
+    # sigma block of the step: channel 0 is the Mott cross-section, total mfp within 1e-6
+    m = o.Material('Si')
+    sig, mfp = eng.test_sigmas(E[:4000])
+    ref_s = np.array([o.sigmas_ds(float(e), m, 10., 'Mott', ot) for e in E[:4000]])
+    assert relerr(sig[:, 0], ref_s[:, 0]).max() < REL
+    ok = E[:4000] > 15000.
+    ref_mfp = np.array([o.mfp_from_sigma(sum(r), m.atnd) for r in ref_s[ok]])
+    assert relerr(mfp[ok], ref_mfp).max() < 2e-6
+    eng.close()
+
+
+def test_mott_DS_trajectories_vs_reference_golden():
+    """Whole DS trajectories with 'Mott' as the elastic channel follow the reference's own run on the same Philox
+    uniforms event for event (type label 'Mott' = channel 0)."""
+    g = np.load(os.path.join(GOLD, 'traj_DS_Si_mott.npz'))
+    eng, _ = _mott_engine()
+    assert eng.channel_names[0] == 'Mott'
+    res, same = _golden_traj_check(eng, g, g['ids'])
+    sc = res.sorted_scats()
+    assert int((sc['type'] == 0).sum()) == int(g['n_mott'])
+    # a run without row recording (plain kernel: elastic = Mott has no per-cell records) gives the same els rows
+    eng2, _ = _mott_engine(scatter_output=[])
+    r2 = eng2.run(count=len(g['ids']), first_id=int(g['ids'][0]))
+    assert np.array_equal(r2.els, res.els) and eng2.launch_info()['launches_per_run'] == 1
+    eng2.close()
+    eng.close()
+
+
+def test_mott_statistics_and_refusals():
+    """A Mott run against the float64 Python oracle on other electrons (backscatter coefficient within 3 sigma);
+    continuous mode and a missing table are refused like the reference fails on them."""
+    from mcdiscrete_b200.engine import Engine
+    from mcdiscrete_b200._lib import MCDError
+    eng, _ = _mott_engine(scatter_output=[])
+    n_gpu = 200000
+    res = eng.run(count=n_gpu, first_id=0)
+    assert res.counters['electrons_done'] == n_gpu
+    ip = base_input(elastic='Mott')
+    tabs = oracle_tables(golden_tables('Si_15k_small'))
+    tabs['Mott'] = o.MottTable(14, 'Si', MOTT_PATH).read_ioffe().to_prob_table()
+    n_ref = 1500
+    els = o.run_electrons(ip, 10 ** 7, n_ref, 12345, tabs)
+    eta_r = np.mean([e.els[0][0] == 'bks' for e in els])
+    eta_g = float((res.outcome == 1).mean())
+    sd = math.sqrt(eta_r * (1 - eta_r) * (1. / n_gpu + 1. / n_ref))
+    print('Mott eta gpu %.4f oracle %.4f (sd %.4f)' % (eta_g, eta_r, sd))
+    assert abs(eta_g - eta_r) < 3.5 * sd, (eta_g, eta_r, sd)
+    # mean number of events per electron against the oracle's (4 standard errors)
+    ne = np.array([len(e.scats) for e in els], float)
+    assert abs(res.counters['events'] / n_gpu - ne.mean()) < 4 * ne.std() / math.sqrt(n_ref)
+    eng.close()
+    with pytest.raises(NotImplementedError):
+        Engine(base_input(elastic='Mott', mode='cont'), device=0)
+    e3 = make_engine(elastic='Mott')
+    upload_golden(e3, golden_tables('Si_15k_small'))
+    with pytest.raises(MCDError):
+        e3.run(count=10, first_id=0)                    # no Mott table uploaded
+    e3.close()
+    e4 = make_engine(elastic='Mott', E0=40000., Emin=30000.)
+    from mcdiscrete_b200.extFunctions import mottTable
+    with pytest.raises(MCDError):
+        mottTable(14, 'Si', MOTT_PATH).upload(e4)       # table ends at 30 keV (IndexError in the reference)
+    e4.close()
+
+
 @pytest.mark.parametrize('scat', [[], ['type', 'energy']])
 def test_accumulated_pipeline_statistics_equal_one_run(scat):
     """run_batches(accumulate=True) + pipeline_stats(): the histogram||counter block of a run split into pipelined
