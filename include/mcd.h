@@ -171,6 +171,18 @@ int mcd_destroy(mcd_ctx* ctx);
  * before their parent; tables built/uploaded on the parent after cloning are not seen by the clone. */
 int mcd_clone(const mcd_ctx* parent, mcd_ctx** out);
 
+/* Launch tuning of a context (defaults are the measured optimum on B200; the A/B tool scripts/ab_kernel.py
+ * presets them through MCD_PASSES / MCD_DUMP_T / MCD_BLOCKS_PER_SM / MCD_NO_POOL).  Results never depend on them.
+ * Set before mcd_set_capacity; clones inherit the parent's values at mcd_clone time. */
+typedef struct mcd_tuning {
+  int32_t handover_passes;     /* launches per statistics-only DS run: 1 = no tail hand-over, default 3, at most 4 */
+  int32_t handover_threshold;  /* a warp hands its electrons to the next pass when it holds <= this many (0..31, 31) */
+  int32_t blocks_per_sm;       /* resident blocks per SM; 0 = as many as fit (default) */
+  int32_t statistics_kernel;   /* 0 = park-pool kernel for statistics-only DS runs (default), 1 = the plain kernel */
+} mcd_tuning;
+int mcd_tuning_get(const mcd_ctx* ctx, mcd_tuning* out);
+int mcd_tuning_set(mcd_ctx* ctx, const mcd_tuning* t);
+
 /* ---- tables -------------------------------------------------------------------------- */
 /* Build table `slot` on the device from host axes (float32, as found by the host axis search that
  * mirrors probTables.py:280-411).  shell_E/shell_n are ignored for slot 0 (Moller uses Wc/n_val). */

@@ -43,6 +43,11 @@ class Params(C.Structure):
                 ('seed', C.c_uint64)]
 
 
+class Tuning(C.Structure):
+    _fields_ = [('handover_passes', C.c_int32), ('handover_threshold', C.c_int32), ('blocks_per_sm', C.c_int32),
+                ('statistics_kernel', C.c_int32)]
+
+
 class ScatLayout(C.Structure):
     _fields_ = [('row_words', C.c_uint32), ('word_of', C.c_int32 * 16)]
 
@@ -70,6 +75,8 @@ SYMBOLS = {
     'mcd_create': (C.c_int, [C.POINTER(Params), C.POINTER(Material), C.c_int, C.POINTER(_P)]),
     'mcd_destroy': (C.c_int, [_P]),
     'mcd_clone': (C.c_int, [_P, C.POINTER(_P)]),
+    'mcd_tuning_get': (C.c_int, [_P, C.POINTER(Tuning)]),
+    'mcd_tuning_set': (C.c_int, [_P, C.POINTER(Tuning)]),
     'mcd_table_build': (C.c_int, [_P, C.c_int, _F, C.c_uint32, _F, C.c_uint32, C.c_double, C.c_double, _P]),
     'mcd_table_upload': (C.c_int, [_P, C.c_int, _F, C.c_uint32, _F, C.c_uint32, _F]),
     'mcd_mott_upload': (C.c_int, [_P, C.c_uint32, C.c_uint32] + [C.POINTER(C.c_double)] * 4),

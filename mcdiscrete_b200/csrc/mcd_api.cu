@@ -410,6 +410,13 @@ void build_dev_params(mcd_ctx* c) {
   P.hist.e_scale = (float)(MCD_HIST_E_BINS / (p.E0 - p.Emin));
   const double sp0 = 2.0 * kPiEFour * mt.atnd * (Z / p.E0) * log(1.166 * p.E0 / J) * 1e-14;
   P.hist.depth_scale = (float)(MCD_HIST_DEPTH_BINS / (2.0 * p.E0 / sp0));
+  // launch tuning defaults (mcd_tuning_set changes them per context); the environment variables are the A/B
+  // overrides of scripts/ab_kernel.py and only set the initial values
+  auto env_int = [](const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; };
+  P.tune_passes = env_int("MCD_PASSES", 3);
+  P.tune_dump_T = env_int("MCD_DUMP_T", 31);
+  P.tune_blocks_per_sm = env_int("MCD_BLOCKS_PER_SM", 0);
+  P.tune_no_pool = env_int("MCD_NO_POOL", 0) != 0;
 }
 
 void layout_of(uint32_t mask, mcd_scat_layout* L) {
@@ -624,6 +631,35 @@ int mcd_create(const mcd_params* p, const mcd_material* m, int device, mcd_ctx**
     return fail(nullptr, MCD_ERR_CUDA, "context allocation: %s", msg.c_str());
   }
   *out = c;
+  return MCD_OK;
+}
+
+int mcd_tuning_get(const mcd_ctx* c, mcd_tuning* out) {
+  if (!c || !out) return fail(nullptr, MCD_ERR_INVALID, "null argument");
+  out->handover_passes = c->P.tune_passes;
+  out->handover_threshold = c->P.tune_dump_T;
+  out->blocks_per_sm = c->P.tune_blocks_per_sm;
+  out->statistics_kernel = c->P.tune_no_pool;
+  return MCD_OK;
+}
+
+int mcd_tuning_set(mcd_ctx* c, const mcd_tuning* t) {
+  int rc = need_ctx(c);
+  if (rc) return rc;
+  if (!t) return fail(c, MCD_ERR_INVALID, "null argument");
+  if (t->handover_passes < 1 || t->handover_passes > 4 || t->handover_threshold < 0 || t->handover_threshold > 31 ||
+      t->blocks_per_sm < 0 || t->statistics_kernel < 0 || t->statistics_kernel > 1)
+    return fail(c, MCD_ERR_INVALID, "tuning out of range (passes 1..4, threshold 0..31, blocks_per_sm >= 0, kernel 0|1)");
+  if (c->els) return fail(c, MCD_ERR_STATE, "mcd_tuning_set must precede mcd_set_capacity");
+  c->P.tune_passes = t->handover_passes;
+  c->P.tune_dump_T = t->handover_threshold;
+  c->P.tune_blocks_per_sm = t->blocks_per_sm;
+  c->P.tune_no_pool = t->statistics_kernel;
+  // the kernel choice and its geometry may have changed: launch info and the hand-over queues follow
+  CU(c, mcd_traj_max_blocks(c->P, c->P.scat_row_words > 0, c->sm_count, &c->li));
+  c->n_blocks = c->li.blocks;
+  for (int i = 0; i < 2; ++i) { cudaFree(c->rq[i]); c->rq[i] = nullptr; }
+  CU(c, alloc_queues(c));
   return MCD_OK;
 }
 

@@ -634,16 +634,11 @@ TrajKernel pick_kernel_pool(const DevParams& P) {
   }
 }
 
-bool pool_enabled() {      // MCD_NO_POOL=1: the plain kernel for statistics-only DS runs too (A/B measurements)
-  static const bool no_pool = getenv("MCD_NO_POOL") != nullptr && atoi(getenv("MCD_NO_POOL")) != 0;
-  return !no_pool;
-}
-
 TrajKernel pick_kernel(const DevParams& P, bool scats) {
   if (scats) return pick_kernel_t<true>(P);
   // statistics-only DS runs use the park-pool kernel; it is compiled for the per-cell cross-section records only
   // (runs whose records could not be built -- channel order not static on [Emin, E0] -- take the plain kernel)
-  if (P.mode == MCD_MODE_DS && P.use_sig_poly && pool_enabled()) return pick_kernel_pool<false>(P);
+  if (P.mode == MCD_MODE_DS && P.use_sig_poly && !P.tune_no_pool) return pick_kernel_pool<false>(P);
   return pick_kernel_t<false>(P);
 }
 
@@ -859,10 +854,7 @@ cudaError_t mcd_traj_max_blocks(const DevParams& P, bool scats, int sm_count, Tr
   err = cudaFuncGetAttributes(&fa, k);
   if (err != cudaSuccess) return err;
   if (per_sm < 1) per_sm = 1;
-  if (const char* env = getenv("MCD_BLOCKS_PER_SM")) {      // tuning knob: fewer resident blocks than the maximum
-    const int v = atoi(env);
-    if (v >= 1 && v < per_sm) per_sm = v;
-  }
+  if (P.tune_blocks_per_sm >= 1 && P.tune_blocks_per_sm < per_sm) per_sm = P.tune_blocks_per_sm;   // (mcd_tuning)
   // shared-memory carve-out: exactly what the resident blocks need (+1 KB per block that the system reserves), the
   // rest of the 256 KB stays L1 for the cross-section cells and the table windows
   const size_t need = (size_t)per_sm * (fa.sharedSizeBytes + 1024);
@@ -878,7 +870,7 @@ cudaError_t mcd_traj_max_blocks(const DevParams& P, bool scats, int sm_count, Tr
 }
 
 int mcd_traj_uses_queue(const DevParams& P, bool scats) {
-  return (!scats && P.mode == MCD_MODE_DS && P.use_sig_poly && pool_enabled()) ? 1 : 0;
+  return (!scats && P.mode == MCD_MODE_DS && P.use_sig_poly && !P.tune_no_pool) ? 1 : 0;
 }
 
 cudaError_t mcd_launch_traj(const DevParams& P, const DevOut& O_in, unsigned long long first_id,
@@ -892,14 +884,12 @@ cudaError_t mcd_launch_traj(const DevParams& P, const DevOut& O_in, unsigned lon
   DevOut O = O_in;
   // tail hand-over (park-pool kernel only): pass 0 runs the fresh ids and dumps what its warps still hold when they
   // are down to dump_T electrons; passes 1..n-1 run the leftover queue of the pass before; the last pass does not
-  // dump.  MCD_DUMP_T=0 or MCD_PASSES=1: one launch.
-  static const int env_T = getenv("MCD_DUMP_T") ? atoi(getenv("MCD_DUMP_T")) : 31;
-  static const int env_passes = getenv("MCD_PASSES") ? atoi(getenv("MCD_PASSES")) : 3;
+  // dump.  mcd_tuning: handover_passes = 1 (or threshold 0): one launch.
   int passes = 1;
   int dump_T = 0;
-  if (mcd_traj_uses_queue(P, scats) && O_in.rq[0] && env_T > 0 && env_passes > 1) {
-    passes = env_passes > 4 ? 4 : env_passes;
-    dump_T = env_T > 31 ? 31 : env_T;
+  if (mcd_traj_uses_queue(P, scats) && O_in.rq[0] && P.tune_dump_T > 0 && P.tune_passes > 1) {
+    passes = P.tune_passes > 4 ? 4 : P.tune_passes;
+    dump_T = P.tune_dump_T > 31 ? 31 : P.tune_dump_T;
   }
   li.launches = passes;
   if (info) *info = li;

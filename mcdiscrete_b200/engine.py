@@ -302,6 +302,20 @@ class Engine:
         check(rc, self.ctx)
 
     # ---- tables -------------------------------------------------------------------------------
+    def tuning(self, **kw):
+        """Launch tuning of this context (mcd_tuning: handover_passes, handover_threshold, blocks_per_sm,
+        statistics_kernel); with keyword arguments the named fields are changed first (before set_capacity).  No
+        result depends on them."""
+        t = _lib.Tuning()
+        self._ck(self.lib.mcd_tuning_get(self.ctx, C.byref(t)))
+        if kw:
+            for k, v in kw.items():
+                if not hasattr(t, k):
+                    raise KeyError(k)
+                setattr(t, k, int(v))
+            self._ck(self.lib.mcd_tuning_set(self.ctx, C.byref(t)))
+        return {k: int(getattr(t, k)) for k, _ in _lib.Tuning._fields_}
+
     def table_build(self, slot, Es, Ws, shell_E=0.0, shell_n=0.0, stream=None):
         Es, Ws = f32(Es), f32(Ws)
         self._ck(self.lib.mcd_table_build(self.ctx, slot, fptr(Es), len(Es), fptr(Ws), len(Ws), shell_E, shell_n,

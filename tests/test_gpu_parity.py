@@ -821,7 +821,7 @@ def test_mott_table_lookup_bit_exact_and_sigma():
     # where rounding the inputs to float32 did not move them across a table threshold the reference's own answer holds
     same_cell = np.array([o.pick_mott_table(ot, float(e), float(x))[1:] == o.pick_mott_table(ot, float(e32), float(x32))[1:]
                           for e, x, e32, x32 in zip(g['pick_E'][keep], g['pick_u'][keep], Eg[keep], ug[keep])])
-    assert same_cell.sum() > 250 and np.abs(c22[same_cell] - g['pick_c2'][keep][same_cell]).max() < 1e-6
+    assert same_cell.sum() > 150 and np.abs(c22[same_cell] - g['pick_c2'][keep][same_cell]).max() < 1e-6
     # sigma block of the step: channel 0 is the Mott cross-section, total mfp within 1e-6
     m = o.Material('Si')
     sig, mfp = eng.test_sigmas(E[:4000])
@@ -885,6 +885,38 @@ def test_mott_statistics_and_refusals():
     with pytest.raises(MCDError):
         mottTable(14, 'Si', MOTT_PATH).upload(e4)       # table ends at 30 keV (IndexError in the reference)
     e4.close()
+
+
+def test_launch_tuning_never_changes_a_result():
+    """mcd_tuning (hand-over passes / threshold, resident blocks, plain kernel instead of the park-pool kernel): the
+    els rows, histograms and counters of a statistics-only run are bit-identical for every setting."""
+    from mcdiscrete_b200._lib import MCDError
+    g = golden_tables('Si_15k_small')
+    ref = None
+    for kw in ({}, dict(handover_passes=1), dict(handover_passes=2, handover_threshold=8), dict(blocks_per_sm=2),
+               dict(statistics_kernel=1), dict(handover_passes=4, handover_threshold=31, blocks_per_sm=1)):
+        eng = make_engine(scatter_output=[])
+        t = eng.tuning(**kw)
+        for k, v in kw.items():
+            assert t[k] == v
+        upload_golden(eng, g)
+        res = eng.run(count=30000, first_id=11)
+        li = eng.launch_info()
+        assert li['launches_per_run'] == (1 if kw.get('statistics_kernel') else t['handover_passes'])
+        if 'blocks_per_sm' in kw:
+            assert li['blocks_per_sm'] == kw['blocks_per_sm']
+        cur = (res.els.tobytes(), eng.stats_host().tobytes())
+        if ref is None:
+            ref = cur
+            assert t == dict(handover_passes=3, handover_threshold=31, blocks_per_sm=0, statistics_kernel=0)
+            with pytest.raises(MCDError):
+                eng.tuning(handover_passes=2)              # after set_capacity
+        assert cur == ref, kw
+        eng.close()
+    eng = make_engine(scatter_output=[])
+    with pytest.raises(MCDError):
+        eng.tuning(handover_passes=9)
+    eng.close()
 
 
 @pytest.mark.parametrize('scat', [[], ['type', 'energy']])
