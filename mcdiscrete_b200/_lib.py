@@ -132,7 +132,12 @@ def load():
                           '(nvcc, sm_100a).  mcdiscrete_b200 has no CPU fallback.' % LIB_PATH)
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SYMBOLS.items():
-        fn = getattr(lib, name)
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:
+            if os.environ.get('MCD_LIB'):          # an older build variant in an A/B run: it simply lacks the call
+                continue
+            raise
         fn.restype = res
         fn.argtypes = args
     if lib.mcd_abi_version() != 1:

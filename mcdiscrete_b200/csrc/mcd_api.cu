@@ -1026,7 +1026,8 @@ static int order_impl(mcd_ctx* c, void* stream, bool columns) {
   c->col_stride = columns ? ((c->rows_total * 4 + 255) / 256) * 256 : 0;
   if (columns && c->P.scat_row_words < 2) return fail(c, MCD_ERR_STATE, "no scats columns");
   CU(c, mcd_launch_order_scats(c->nev, c->last_count, c->tile_tmp, c->offsets, c->total_dev, c->scats, c->chunk_count,
-                               used, c->P.scat_row_words, c->sorted, c->col_stride, nullptr, c->sm_count, s));
+                               used, c->P.scat_row_words, c->sorted, c->col_stride,
+                               columns ? (c->col_stride >> 2) : c->sorted_cap_rows, nullptr, c->sm_count, s));
   unsigned long long total = 0;
   CU(c, cudaMemcpyAsync(&total, c->total_dev, sizeof total, cudaMemcpyDeviceToHost, s));
   CU(c, cudaStreamSynchronize(s));
@@ -1063,7 +1064,8 @@ int mcd_order_scats_columns_enqueue(mcd_ctx* c, void* stream) {
   }
   c->col_stride = stride;
   CU(c, mcd_launch_order_scats(c->nev, c->last_count, c->tile_tmp, c->offsets, c->total_dev, c->scats, c->chunk_count,
-                               c->n_chunks, c->P.scat_row_words, c->sorted, c->col_stride, c->chunk_next, c->sm_count, s));
+                               c->n_chunks, c->P.scat_row_words, c->sorted, c->col_stride, c->col_stride >> 2,
+                               c->chunk_next, c->sm_count, s));
   c->ordered = 3;
   return MCD_OK;
 }

@@ -33,9 +33,10 @@ int mcd_traj_uses_queue(const DevParams& P, bool scats);     // 1 if mcd_launch_
 cudaError_t mcd_launch_order_scats(const unsigned int* nev, unsigned long long count, unsigned long long* tile_tmp,
                                    unsigned long long* offsets, unsigned long long* total_dev, const uint32_t* pool,
                                    const unsigned int* chunk_count, unsigned int nchunks, int row_words,
-                                   uint32_t* sorted, unsigned long long col_stride, const unsigned int* nchunks_dev,
-                                   int sm_count, cudaStream_t stream);
-// col_stride != 0: columnar output (scatter_cols); nchunks_dev (columnar only): device word holding the used chunks
+                                   uint32_t* sorted, unsigned long long col_stride, unsigned long long max_rows,
+                                   const unsigned int* nchunks_dev, int sm_count, cudaStream_t stream);
+// col_stride != 0: columnar output; max_rows: rows the output holds (targets beyond it are skipped); nchunks_dev
+// (enqueued columnar regrouping only): device word holding the used chunks
 unsigned long long mcd_order_tiles(unsigned long long count);
 
 // mcd_tables.cu

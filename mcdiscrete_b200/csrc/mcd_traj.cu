@@ -727,63 +727,36 @@ __global__ void scan_apply(const unsigned int* __restrict__ nev, unsigned long l
   if (base <= n && n < base + kScanItems) offsets[n] = run - 0;       // offsets[n] = total (set by the owner of n)
 }
 
-// every stored row of the chunk pool goes to sorted[offsets[rel_id] + event].  One block per chunk (1024 rows), one
-// row per thread and pass; rows are moved as 8-byte words when the row length allows (row starts are then 8-byte
-// aligned in both buffers), so a 24-byte row is three loads and three stores.
-__global__ void __launch_bounds__(256) scatter_rows(const uint32_t* __restrict__ pool,
-                                                    const unsigned int* __restrict__ chunk_count, unsigned int nchunks,
-                                                    int row_words, const unsigned long long* __restrict__ offsets,
-                                                    uint32_t* __restrict__ sorted) {
-  for (unsigned int c = blockIdx.x; c < nchunks; c += gridDim.x) {
-    const unsigned int cnt = chunk_count[c];
-    const uint32_t* cbase = pool + (size_t)c * MCD_CHUNK_ROWS * (size_t)row_words;
-    if ((row_words & 1) == 0) {
-      const int rw2 = row_words >> 1;
-      for (unsigned int r = threadIdx.x; r < cnt; r += blockDim.x) {
-        const uint2* src = reinterpret_cast<const uint2*>(cbase) + (size_t)r * rw2;
-        const uint2 head = __ldcs(src);
-        const unsigned long long d = offsets[head.x] + (unsigned long long)(head.y & 0xffffffu);
-        uint2* dst = reinterpret_cast<uint2*>(sorted) + d * (unsigned long long)rw2;
-        dst[0] = head;
-        for (int w = 1; w < rw2; ++w) dst[w] = __ldcs(src + w);
-      }
-    } else {
-      for (unsigned int r = threadIdx.x; r < cnt; r += blockDim.x) {
-        const uint32_t* src = cbase + (size_t)r * row_words;
-        const uint32_t rel = src[0], w1 = src[1];
-        uint32_t* dst = sorted + (offsets[rel] + (unsigned long long)(w1 & 0xffffffu)) * (unsigned long long)row_words;
-        dst[0] = rel;
-        dst[1] = w1;
-        for (int w = 2; w < row_words; ++w) dst[w] = src[w];
-      }
-    }
-  }
-}
-
-// Columnar variant: the payload words 2.. of every row go to one float column each (column j = word 2+j at byte
-// offset j * col_stride) and the channel index to a byte column; row d of every column = the event offsets[rel_id] +
-// event.  Words 0/1 (electron id, event index) are NOT stored: in trajectory order they follow from the offsets.
+// Regrouping of the appended rows (mcd_order_scats / mcd_order_scats_columns): every stored row of the chunk pool goes
+// to position d = offsets[rel_id] + event of the output.
 //
 // One block per chunk.  The chunk (<= 1024 rows, contiguous) is staged in shared memory with coalesced loads, then
 // read back TRANSPOSED: a warp of the trajectory kernel appends the rows of one loop iteration side by side (lane
 // order) and all 32 lanes are alive until the ids run out, so rows i, i+32, i+64, ... of a chunk are consecutive
-// events of ONE electron and land in consecutive column entries.  Lane t of a warp therefore takes row t*32 + r: the
-// 32 stores of a column instruction hit one or two 128-byte lines instead of 32 different ones (the row-at-a-time
-// version wrote 2.6x its payload and read 3.2x).  Nothing depends on that structure for correctness:
-// every row still computes its own destination.  Shared-memory rows are skewed by one word per 32 rows so that the
-// transposed reads (stride 32 rows) fall on 32 different banks.
-__global__ void __launch_bounds__(256) scatter_cols(const uint32_t* __restrict__ pool,
-                                                    const unsigned int* __restrict__ chunk_count, unsigned int nchunks,
-                                                    int row_words, const unsigned long long* __restrict__ offsets,
-                                                    unsigned char* __restrict__ cols, unsigned long long col_stride,
-                                                    const unsigned int* __restrict__ nchunks_dev) {
+// events of ONE electron and land in consecutive output positions.  Lane t of a warp therefore takes row t*32 + r:
+// the 32 stores of one instruction hit one or two 128-byte lines (columns) or one contiguous run of rows (row-major)
+// instead of 32 different places (the row-at-a-time version wrote 2.6x its payload and read 3.2x).
+// Nothing depends on that structure for correctness: every row still computes its own destination.  Shared-memory
+// rows are skewed by one word per 32 rows so that the transposed reads (stride 32 rows) fall on 32 different banks.
+//
+// COLS = false: packed rows in trajectory order.
+// COLS = true: the payload words 2.. of every row go to one float column each (column j = word 2+j at byte offset
+// j * col_stride) and the channel index to a byte column.  Words 0/1 (electron id, event index) are NOT stored: in
+// trajectory order they follow from the offsets.
+template <bool COLS>
+__global__ void __launch_bounds__(256) scatter_chunks(const uint32_t* __restrict__ pool,
+                                                      const unsigned int* __restrict__ chunk_count, unsigned int nchunks,
+                                                      int row_words, const unsigned long long* __restrict__ offsets,
+                                                      unsigned char* __restrict__ out, unsigned long long col_stride,
+                                                      unsigned long long max_rows,
+                                                      const unsigned int* __restrict__ nchunks_dev) {
   extern __shared__ uint32_t s_rows[];                     // MCD_CHUNK_ROWS * row_words + 32 words
-  // rows per column: a run that dropped rows (pool overflow; the caller re-runs it) has event counts beyond the
-  // stored rows -- such targets are skipped instead of written past the columns
-  const unsigned long long max_rows = col_stride >> 2;
+  // max_rows: a run that dropped rows (pool overflow; the caller re-runs it) has event counts beyond the stored
+  // rows -- such targets are skipped instead of written past the output
   // enqueued right behind the trajectory kernel (no host round trip): the number of used chunks is still on the device
   if (nchunks_dev) nchunks = min(nchunks, *nchunks_dev);
-  unsigned char* type_col = cols + (unsigned long long)(row_words - 2) * col_stride;
+  unsigned char* type_col = out + (unsigned long long)(row_words - 2) * col_stride;
+  uint32_t* sorted = reinterpret_cast<uint32_t*>(out);
   const unsigned int lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const unsigned int rw = (unsigned int)row_words;
   for (unsigned int c = blockIdx.x; c < nchunks; c += gridDim.x) {
@@ -803,9 +776,14 @@ __global__ void __launch_bounds__(256) scatter_cols(const uint32_t* __restrict__
       const uint32_t rel = src[0], w1 = src[1];
       const unsigned long long d = offsets[rel] + (unsigned long long)(w1 & 0xffffffu);
       if (d >= max_rows) continue;
-      type_col[d] = (unsigned char)(w1 >> 24);
-      for (unsigned int w = 2; w < rw; ++w)
-        reinterpret_cast<uint32_t*>(cols + (unsigned long long)(w - 2) * col_stride)[d] = src[w];
+      if (COLS) {
+        type_col[d] = (unsigned char)(w1 >> 24);
+        for (unsigned int w = 2; w < rw; ++w)
+          reinterpret_cast<uint32_t*>(out + (unsigned long long)(w - 2) * col_stride)[d] = src[w];
+      } else {
+        uint32_t* dst = sorted + d * (unsigned long long)rw;
+        for (unsigned int w = 0; w < rw; ++w) dst[w] = src[w];
+      }
     }
   }
 }
@@ -815,8 +793,8 @@ __global__ void __launch_bounds__(256) scatter_cols(const uint32_t* __restrict__
 cudaError_t mcd_launch_order_scats(const unsigned int* nev, unsigned long long count, unsigned long long* tile_tmp,
                                    unsigned long long* offsets, unsigned long long* total_dev, const uint32_t* pool,
                                    const unsigned int* chunk_count, unsigned int nchunks, int row_words,
-                                   uint32_t* sorted, unsigned long long col_stride, const unsigned int* nchunks_dev,
-                                   int sm_count, cudaStream_t stream) {
+                                   uint32_t* sorted, unsigned long long col_stride, unsigned long long max_rows,
+                                   const unsigned int* nchunks_dev, int sm_count, cudaStream_t stream) {
   const unsigned long long per_tile = (unsigned long long)kScanT * kScanItems;
   const unsigned int ntiles = (unsigned int)((count + 1 + per_tile - 1) / per_tile);
   scan_tile_sums<<<ntiles, kScanT, 0, stream>>>(nev, count, tile_tmp);
@@ -824,16 +802,14 @@ cudaError_t mcd_launch_order_scats(const unsigned int* nev, unsigned long long c
   scan_apply<<<ntiles, kScanT, 0, stream>>>(nev, count, tile_tmp, offsets);
   if (sorted && nchunks) {
     const unsigned int grid = nchunks < (unsigned int)(sm_count * 64) ? nchunks : (unsigned int)(sm_count * 64);
-    if (col_stride) {
-      const size_t smem = ((size_t)MCD_CHUNK_ROWS * (size_t)row_words + 32) * sizeof(uint32_t);   // 24.1 .. 56.1 KB
-      if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(scatter_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-      }
-      scatter_cols<<<grid, 256, smem, stream>>>(pool, chunk_count, nchunks, row_words, offsets,
-                                                reinterpret_cast<unsigned char*>(sorted), col_stride, nchunks_dev);
-    } else
-      scatter_rows<<<grid, 256, 0, stream>>>(pool, chunk_count, nchunks, row_words, offsets, sorted);
+    const size_t smem = ((size_t)MCD_CHUNK_ROWS * (size_t)row_words + 32) * sizeof(uint32_t);     // 24.1 .. 56.1 KB
+    auto kern = col_stride ? scatter_chunks<true> : scatter_chunks<false>;
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+    }
+    kern<<<grid, 256, smem, stream>>>(pool, chunk_count, nchunks, row_words, offsets, reinterpret_cast<unsigned char*>(sorted),
+                                      col_stride, max_rows, nchunks_dev);
   }
   return cudaGetLastError();
 }
