@@ -274,13 +274,15 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device: mcdiscrete_b200 has no CPU fallback')
     torch.cuda.set_device(local)
+    from mcdiscrete_b200.distributed import allreduce_stats, rank_range, bind_to_gpu, restore_affinity
+    # N > 1: every rank next to its own GPU (pinned host buffers on that NUMA node); one rank keeps the whole box
+    binding = bind_to_gpu(local) if world > 1 else {'bound': False, 'why': 'single rank'}
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     from mcdiscrete_b200 import _lib
     from mcdiscrete_b200.engine import Engine
     from mcdiscrete_b200.probTables import genTables
-    from mcdiscrete_b200.distributed import allreduce_stats, rank_range
     import ctypes as C
     n_stats = _lib.HIST_TOTAL + C.sizeof(_lib.Counters) // 8
 
@@ -644,8 +646,10 @@ def main():
                         'nan_clamped': cnt['nan_clamped'], 'headline_stats_sha1': headline_sha},
             'legs': leg,
         }
+        out['host_binding'] = {k: v for k, v in binding.items() if not k.startswith('_')}
         if not args.no_cpu:
-            cores = os.cpu_count() or 1
+            restore_affinity(binding)                     # the CPU leg uses every core of the box
+            cores = len(os.sched_getaffinity(0)) or 1
             el_s, ev_s, dtc, _ = cpu_sample(2000000, cores)
             out['cpu_baseline'] = {'value': el_s, 'unit': 'electrons/s', 'cores': cores, 'kind': 'port',
                                    'events_per_s': ev_s,

@@ -221,6 +221,7 @@ int build_sig_poly(mcd_ctx* c, const int* order) {
         }
       }
     }
+    if (getenv("MCD_DEBUG")) fprintf(stderr, "[mcd] sig_poly logM=%d worst=%.3g\n", logM, worst);
     if (worst < 1.5e-7) {
       cudaFree(c->sig_poly); c->sig_poly = nullptr;
       if (cudaMalloc(&c->sig_poly, poly.size() * sizeof(float4)) != cudaSuccess) return 0;
@@ -295,6 +296,7 @@ int build_sig_hot(mcd_ctx* c, const int* order) {
         worst_tot = fmax(worst_tot, fabs((double)fmaf(fmaf((float)q2, xf, (float)q1), xf, (float)q0) - ref[T]) / ref[T]);
       }
     }
+    if (getenv("MCD_DEBUG")) fprintf(stderr, "[mcd] sig_hot logM=%d worst_lin=%.3g worst_tot=%.3g\n", logM, worst_lin, worst_tot);
     if (worst_lin < 1.5e-6 && worst_tot < 1.5e-7) {
       cudaFree(c->sig_hot); c->sig_hot = nullptr;
       if (cudaMalloc(&c->sig_hot, hot.size() * sizeof(float4)) != cudaSuccess) return 0;
@@ -607,6 +609,7 @@ int mcd_create(const mcd_params* p, const mcd_material* m, int device, mcd_ctx**
     cudaGetLastError();
   }
   build_dev_params(c);
+  if (getenv("MCD_DEBUG")) fprintf(stderr, "[mcd] order_static=%d\n", c->P.order_static);
   c->P.use_sig_poly = 0;
   if (p->mode == MCD_MODE_DS && c->P.order_static && !getenv("MCD_NO_SIGPOLY"))
     c->P.use_sig_poly = build_sig_poly(c, c->slot_order) && build_sig_hot(c, c->slot_order);

@@ -11,6 +11,51 @@ def rank_range(num_el, rank, world):
     return lo, hi - lo
 
 
+def bind_to_gpu(local_rank):
+    """Pin this process to the CPUs next to its GPU (NVML's ideal CPU set = the NUMA node of the GPU's PCIe root) so
+    that the pinned host buffers of the drain are allocated on that node (first touch) and the D2H copies of the
+    ranks do not all cross the socket interconnect: with 8 unbound ranks the aggregated D2H rate of one box was 90 GB/s
+    (1.6x one link), profiles/rnd2m_bench_8gpu.json.  Returns a dict describing what was done; never raises
+    (MCD_NO_BIND=1 or a restricted cpuset: nothing is changed).  `restore_affinity(info)` undoes it."""
+    info = {'bound': False}
+    if os.environ.get('MCD_NO_BIND'):
+        info['why'] = 'MCD_NO_BIND'
+        return info
+    try:
+        import pynvml
+        import torch
+        before = sorted(os.sched_getaffinity(0))
+        info['before'] = len(before)
+        pynvml.nvmlInit()
+        try:
+            pr = torch.cuda.get_device_properties(local_rank)
+            bus = '%08x:%02x:%02x.0' % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        want = sorted(cpus & set(before))
+        if want and len(want) < len(before):
+            os.sched_setaffinity(0, want)
+            info.update(bound=True, cpus=len(want), first_cpu=want[0], last_cpu=want[-1], _restore=before)
+        else:
+            info['why'] = 'ideal CPU set covers the whole allowed set' if want else 'ideal CPUs are outside the cpuset'
+    except Exception as ex:                                   # noqa: BLE001 -- binding is an optimisation only
+        info['why'] = '%s: %s' % (type(ex).__name__, ex)
+    return info
+
+
+def restore_affinity(info):
+    """Give the process its original CPU set back (e.g. before a host-side leg that should use every core)."""
+    if info.get('_restore'):
+        try:
+            os.sched_setaffinity(0, info['_restore'])
+        except Exception:                                     # noqa: BLE001
+            pass
+
+
 def init_from_env(backend=None):
     """torch.distributed from torchrun's environment (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_*)."""
     import torch

@@ -43,10 +43,12 @@ def main(argv=None):
     from .engine import Engine
     from .probTables import genTables
     from .store import ResultStore, store_name, have_pytables
-    from .distributed import init_from_env, rank_range, allreduce_stats
+    from .distributed import init_from_env, rank_range, allreduce_stats, bind_to_gpu
     _, inputFile, out, fmt, batch = dealWithInput(sys.argv[1:] if argv is None else argv)
     inputPar = readInput(inputFile)
     rank, local, world = init_from_env()
+    if world > 1:
+        bind_to_gpu(local)                 # pinned staging buffers on the NUMA node of this rank's GPU
     if rank == 0:
         print(' \n - Number of incident electrons: %s' % inputPar['num_el'])
         print(' \n - Material is: %s' % inputPar['material'])

@@ -28,6 +28,9 @@ def main():
     rank, local, world = (int(os.environ.get(k, d)) for k, d in (('RANK', 0), ('LOCAL_RANK', 0), ('WORLD_SIZE', 1)))
     torch.cuda.set_device(local)
     if world > 1:
+        from mcdiscrete_b200.distributed import bind_to_gpu
+        bind_to_gpu(local)
+    if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
 
