@@ -463,21 +463,41 @@ def main():
     h2d = C.sizeof(_lib.Params) + 1024      # launch parameter block: there are no per-step input arrays
     d2h = n_el * 32 + (8 * n_stats) // max(args.steps, 1)
 
+    e2e_marks = []
+
     def e2e_pass(nsteps):
         last = None
+        del e2e_marks[:]
         eng.reset_pipeline_stats()
         for r in eng.run_batches(nsteps * n_el, n_el, first_id=first_id() + 10 ** 12, accumulate=True):
             last = r                                  # rows are in pinned host memory here
             _ = int(r.els['code'][0])
+            e2e_marks.append(time.time())
         tot = eng.pipeline_stats()                    # sum over the pipeline's contexts ...
+        e2e_marks.append(time.time())
         allreduce_stats(tot)                          # ... ONE all-reduce per run
-        return last, tot.cpu().numpy()
+        blk = tot.cpu().numpy()
+        e2e_marks.append(time.time())
+        return last, blk
     e2e_pass(NPIPE + 2)                               # warm every context of the pipeline (device buffers, pinned staging)
     barrier()
     t0 = time.time()
     r, e2e_block = e2e_pass(args.steps)
+    t_done = time.time()
     barrier()
     dt = max_over_ranks(time.time() - t0)
+    # where the end-to-end time goes (host clock, max over ranks): first batch on the host, steady interval between
+    # batches, hand-over of the last batch .. merged statistics, the all-reduce + copy of the block, the final barrier
+    mk = e2e_marks
+    nb_ = len(mk) - 2
+    e2e_detail = {
+        'first_batch_ms': 1e3 * max_over_ranks(mk[0] - t0),
+        'steady_ms_per_step': 1e3 * max_over_ranks((mk[nb_ - 1] - mk[0]) / max(nb_ - 1, 1)),
+        'merge_stats_ms': 1e3 * max_over_ranks(mk[nb_] - mk[nb_ - 1]),
+        'allreduce_and_copy_ms': 1e3 * max_over_ranks(mk[nb_ + 1] - mk[nb_]),
+        'slowest_rank_total_ms': 1e3 * max_over_ranks(t_done - t0),
+        'fastest_rank_total_ms': -1e3 * max_over_ranks(-(t_done - t0)),
+        'wall_ms': 1e3 * dt}
     cnt_e2e = counters_of(e2e_block)
     assert cnt_e2e['electrons_done'] == n_el * world * args.steps
     e2e = n_el * world * args.steps / dt
@@ -636,6 +656,7 @@ def main():
                        'full_output_stats_sha1': leg.get('full_output', {}).get('stats_sha1'),
                        'c5_cells_sha1': leg.get('c5_cells', {}).get('sha1_of_digests')},
             'e2e': {'value': e2e, 'unit': 'electrons/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+            'e2e_detail': e2e_detail,
             'gpu_launches': args.steps * (launches + 1) + (NPIPE - 1),
             'clocks': clocks,
             'roofline': roofline,

@@ -545,7 +545,16 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
         const int room = kPoolSlots - n_ready - n_pend;
         const int r = __popc(pm & lt);
         const int top = kPoolSlots - n_pend - 1;                 // first free slot of the parked stack
-        wst += (uint32_t)min(__popc(pm), room) << 8;             // (before the branches: nothing lives across the call)
+        const int nput = min(__popc(pm), room);
+#ifndef MCD_NO_PARK_TAKE
+        // a lane that parks takes a ready electron of the pool in the same breath (the refill at the top of the loop
+        // then only serves retired lanes and an empty pool): one pool transaction per parked event instead of two
+        const int first_ready = n_ready - 1;
+        const int ntake = min(nput, n_ready);
+        wst += ((uint32_t)nput << 8) - (uint32_t)ntake;          // (before the branches: nothing lives across the call)
+#else
+        wst += (uint32_t)nput << 8;
+#endif
         if (park) {
           if (r < room) {
             uint32_t* w = pool + (top - r) * kSlotWords;
@@ -553,6 +562,13 @@ traj_kernel_pool(const __grid_constant__ DevParams P, const DevOut O, const unsi
             *reinterpret_cast<uint4*>(w + 12) = make_uint4(__float_as_uint(uz), __float_as_uint(uphi), __float_as_uint(ux), __float_as_uint(tot));
             alive = false;
             outcome = -1;
+#ifndef MCD_NO_PARK_TAKE
+            if (r < ntake) {
+              const uint4* q = reinterpret_cast<const uint4*>(pool + (first_ready - r) * kSlotWords);
+              pool_unpack(q[0], q[1], q[2], e, rel_id, ev);
+              alive = true;
+            }
+#endif
           } else {
             // pool full (rare): this lane searches its table at once, like traj_kernel does for every table event
             const float4 r4 = table_event_call<S>(P, e.E, ux, tot, uz, slot, flags);

@@ -428,6 +428,14 @@ class Engine:
         return {'blocks': b.value, 'threads': t.value, 'regs': r.value, 'blocks_per_sm': o.value,
                 'launches_per_run': n.value}
 
+    def enqueue_els_drain(self, count, stream=None):
+        """Enqueue the D2H copy of the els rows of the run just launched on `stream`, behind its kernels, into this
+        context's pinned staging buffer: the copy starts the moment the run ends and overlaps whatever the other
+        contexts of a pipeline are doing.  Returns the (not yet valid) rows; sync(stream) makes them valid."""
+        raw = self._host('els', count * 32, True)
+        self._ck(self.lib.mcd_drain_els(self.ctx, raw.ctypes.data_as(C.c_void_p), 0, count, C.c_void_p(stream or 0)))
+        return raw.view(_lib.EL_ROW_DTYPE)
+
     def drain(self, first_id, count, want_els=True, want_scats=True, pinned=False, stream=None, ordered=False):
         """Copy the rows of the last run to host arrays.  ordered=True regroups the scats rows on the device
         into trajectory order first (mcd_order_scats) and returns them with per-electron offsets;
@@ -586,7 +594,7 @@ class Engine:
         want_els = bool(self.el_cols) if els is None else bool(els)
 
         def finish(p):
-            e, st, first, cnt = p
+            e, st, first, cnt, early = p
             e.sync(st)
             cnts = None
             if e.row_words or not accumulate:
@@ -596,7 +604,9 @@ class Engine:
                 if accumulate:
                     blk = e.stats_host()
                     self._acc_host = blk if getattr(self, '_acc_host', None) is None else self._acc_host + blk
-            if want_els or e.row_words:
+            if early is not None:                          # the copy was enqueued behind the kernel: it is done
+                els_rows, scats = early, {}
+            elif want_els or e.row_words:
                 els_rows, scats = e.drain(first, cnt, want_els=want_els, pinned=True, stream=st, ordered=ordered)
             else:
                 els_rows, scats = None, {}
@@ -617,7 +627,11 @@ class Engine:
                 if on_launched is not None:
                     with torch.cuda.stream(streams[k % depth]):
                         on_launched(e, streams[k % depth])
-                pending.append((e, st, first, cnt))
+                # runs without scats rows: the els rows leave the device right behind the kernel (no host round trip
+                # between the end of the run and the start of its copy; at the end of the job only the LAST batch's
+                # copy is exposed instead of the copies of all `depth` batches still in flight)
+                early = e.enqueue_els_drain(cnt, st) if (want_els and not e.row_words) else None
+                pending.append((e, st, first, cnt, early))
                 if len(pending) == depth:                  # every context is busy: drain the oldest batch
                     yield finish(pending.popleft())
                 k += 1
