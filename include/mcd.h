@@ -179,6 +179,7 @@ typedef struct mcd_tuning {
   int32_t handover_threshold;  /* a warp hands its electrons to the next pass when it holds <= this many (0..31, 31) */
   int32_t blocks_per_sm;       /* resident blocks per SM; 0 = as many as fit (default) */
   int32_t statistics_kernel;   /* 0 = park-pool kernel for statistics-only DS runs (default), 1 = the plain kernel */
+  int32_t tail_priority;       /* 1 = hand-over passes on a high-priority side stream (default), 0 = on the run's stream */
 } mcd_tuning;
 int mcd_tuning_get(const mcd_ctx* ctx, mcd_tuning* out);
 int mcd_tuning_set(mcd_ctx* ctx, const mcd_tuning* t);

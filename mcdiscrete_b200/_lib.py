@@ -45,7 +45,7 @@ class Params(C.Structure):
 
 class Tuning(C.Structure):
     _fields_ = [('handover_passes', C.c_int32), ('handover_threshold', C.c_int32), ('blocks_per_sm', C.c_int32),
-                ('statistics_kernel', C.c_int32)]
+                ('statistics_kernel', C.c_int32), ('tail_priority', C.c_int32)]
 
 
 class ScatLayout(C.Structure):

@@ -76,6 +76,7 @@ struct mcd_ctx {
   std::vector<Run> runs;
   uint64_t rows_total = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  TrajTailStream tail;                        // high-priority side stream of the hand-over passes (mcd_tuning)
   bool timed = false;
   std::string err;
 };
@@ -419,6 +420,7 @@ void build_dev_params(mcd_ctx* c) {
   P.tune_dump_T = env_int("MCD_DUMP_T", 31);
   P.tune_blocks_per_sm = env_int("MCD_BLOCKS_PER_SM", 0);
   P.tune_no_pool = env_int("MCD_NO_POOL", 0) != 0;
+  P.tune_tail_priority = env_int("MCD_TAIL_PRIORITY", 1) != 0;
 }
 
 void layout_of(uint32_t mask, mcd_scat_layout* L) {
@@ -556,6 +558,16 @@ int mcd_device_info(int device, char* name, int name_len, int* sm_count, int* cc
   return MCD_OK;
 }
 
+// the side stream of the hand-over passes: highest priority the device offers, non-blocking
+static cudaError_t alloc_tail_stream(mcd_ctx* c) {
+  int lo = 0, hi = 0;
+  cudaError_t e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  if (e != cudaSuccess) return e;
+  if ((e = cudaStreamCreateWithPriority(&c->tail.stream, cudaStreamNonBlocking, hi)) != cudaSuccess) return e;
+  if ((e = cudaEventCreateWithFlags(&c->tail.first_done, cudaEventDisableTiming)) != cudaSuccess) return e;
+  return cudaEventCreateWithFlags(&c->tail.tail_done, cudaEventDisableTiming);
+}
+
 // leftover queues of the tail hand-over: a warp hands over at most 32 electrons, 12 words each
 static cudaError_t alloc_queues(mcd_ctx* c) {
   if (!mcd_traj_uses_queue(c->P, c->P.scat_row_words > 0)) return cudaSuccess;
@@ -625,7 +637,7 @@ int mcd_create(const mcd_params* p, const mcd_material* m, int device, mcd_ctx**
   }
   c->n_blocks = c->li.blocks;
   if ((e = cudaMalloc(&c->ticket, 8 * sizeof(unsigned long long))) != cudaSuccess || (e = alloc_queues(c)) != cudaSuccess ||
-      (e = cudaMalloc(&c->stats, kStatsWords * 8)) != cudaSuccess ||
+      (e = alloc_tail_stream(c)) != cudaSuccess || (e = cudaMalloc(&c->stats, kStatsWords * 8)) != cudaSuccess ||
       (e = cudaMalloc(&c->chunk_next, sizeof(unsigned int))) != cudaSuccess ||
       (e = cudaMemset(c->stats, 0, kStatsWords * 8)) != cudaSuccess ||
       (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess) {
@@ -643,6 +655,7 @@ int mcd_tuning_get(const mcd_ctx* c, mcd_tuning* out) {
   out->handover_threshold = c->P.tune_dump_T;
   out->blocks_per_sm = c->P.tune_blocks_per_sm;
   out->statistics_kernel = c->P.tune_no_pool;
+  out->tail_priority = c->P.tune_tail_priority;
   return MCD_OK;
 }
 
@@ -651,13 +664,16 @@ int mcd_tuning_set(mcd_ctx* c, const mcd_tuning* t) {
   if (rc) return rc;
   if (!t) return fail(c, MCD_ERR_INVALID, "null argument");
   if (t->handover_passes < 1 || t->handover_passes > 4 || t->handover_threshold < 0 || t->handover_threshold > 31 ||
-      t->blocks_per_sm < 0 || t->statistics_kernel < 0 || t->statistics_kernel > 1)
-    return fail(c, MCD_ERR_INVALID, "tuning out of range (passes 1..4, threshold 0..31, blocks_per_sm >= 0, kernel 0|1)");
+      t->blocks_per_sm < 0 || t->statistics_kernel < 0 || t->statistics_kernel > 1 || t->tail_priority < 0 ||
+      t->tail_priority > 1)
+    return fail(c, MCD_ERR_INVALID, "tuning out of range (passes 1..4, threshold 0..31, blocks_per_sm >= 0, kernel 0|1, "
+                "tail_priority 0|1)");
   if (c->els) return fail(c, MCD_ERR_STATE, "mcd_tuning_set must precede mcd_set_capacity");
   c->P.tune_passes = t->handover_passes;
   c->P.tune_dump_T = t->handover_threshold;
   c->P.tune_blocks_per_sm = t->blocks_per_sm;
   c->P.tune_no_pool = t->statistics_kernel;
+  c->P.tune_tail_priority = t->tail_priority;
   // the kernel choice and its geometry may have changed: launch info and the hand-over queues follow
   CU(c, mcd_traj_max_blocks(c->P, c->P.scat_row_words > 0, c->sm_count, &c->li));
   c->n_blocks = c->li.blocks;
@@ -684,7 +700,7 @@ int mcd_clone(const mcd_ctx* parent, mcd_ctx** out) {
   c->l2_persist_bytes = parent->l2_persist_bytes;
   c->n_blocks = parent->n_blocks;
   if ((e = cudaMalloc(&c->ticket, 8 * sizeof(unsigned long long))) != cudaSuccess || (e = alloc_queues(c)) != cudaSuccess ||
-      (e = cudaMalloc(&c->stats, kStatsWords * 8)) != cudaSuccess ||
+      (e = alloc_tail_stream(c)) != cudaSuccess || (e = cudaMalloc(&c->stats, kStatsWords * 8)) != cudaSuccess ||
       (e = cudaMalloc(&c->chunk_next, sizeof(unsigned int))) != cudaSuccess ||
       (e = cudaMemset(c->stats, 0, kStatsWords * 8)) != cudaSuccess ||
       (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess) {
@@ -707,6 +723,9 @@ int mcd_destroy(mcd_ctx* c) {
   cudaFree(c->stats);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->tail.first_done) cudaEventDestroy(c->tail.first_done);
+  if (c->tail.tail_done) cudaEventDestroy(c->tail.tail_done);
+  if (c->tail.stream) cudaStreamDestroy(c->tail.stream);
   delete c;
   return MCD_OK;
 }
@@ -913,7 +932,7 @@ int mcd_run(mcd_ctx* c, uint64_t first_id, uint64_t count, void* stream) {
     cudaGetLastError();
   }
   CU(c, cudaEventRecord(c->ev0, s));
-  CU(c, mcd_launch_traj(c->P, O, first_id, count, c->sm_count, s, &c->li));
+  CU(c, mcd_launch_traj(c->P, O, first_id, count, c->sm_count, s, &c->li, &c->tail));
   CU(c, cudaEventRecord(c->ev1, s));
   c->last_count = count;
   c->seg_cached = false;

@@ -24,8 +24,15 @@ struct TrajLaunchInfo {
 };
 
 // mcd_traj.cu
+// tail: optional high-priority side stream for the hand-over passes and the histogram pass (+ two events that order
+// it behind the first pass and in front of whatever follows on `stream`); null = everything on `stream`
+struct TrajTailStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t first_done = nullptr, tail_done = nullptr;
+};
 cudaError_t mcd_launch_traj(const DevParams& P, const DevOut& O, unsigned long long first_id,
-                            unsigned long long count, int sm_count, cudaStream_t stream, TrajLaunchInfo* info);
+                            unsigned long long count, int sm_count, cudaStream_t stream, TrajLaunchInfo* info,
+                            const TrajTailStream* tail = nullptr);
 cudaError_t mcd_traj_max_blocks(const DevParams& P, bool scats, int sm_count, TrajLaunchInfo* info);
 cudaError_t mcd_launch_stats_merge(unsigned long long* dst, unsigned long long* src, int n, cudaStream_t stream);
 int mcd_traj_uses_queue(const DevParams& P, bool scats);     // 1 if mcd_launch_traj wants the leftover queues

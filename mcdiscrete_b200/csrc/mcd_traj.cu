@@ -759,6 +759,38 @@ __global__ void scan_apply(const unsigned int* __restrict__ nev, unsigned long l
 // COLS = true: the payload words 2.. of every row go to one float column each (column j = word 2+j at byte offset
 // j * col_stride) and the channel index to a byte column.  Words 0/1 (electron id, event index) are NOT stored: in
 // trajectory order they follow from the offsets.
+// 16-byte asynchronous global -> shared copy (LDGSTS, L2 only: the chunk is read once)
+__device__ __forceinline__ void cp_async16(uint32_t* smem_dst, const uint32_t* gmem_src) {
+  const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+constexpr unsigned int kStageSkew = 4;                     // words of skew per 32 rows (keeps 16-byte units aligned)
+__host__ __device__ constexpr unsigned int stage_words(unsigned int rw) { return MCD_CHUNK_ROWS * rw + 32u * kStageSkew; }
+
+// Stage chunk `c` into `buf`: 16-byte units, unit u holds words 4u .. 4u+3 of the chunk; 32 rows = 8 rw units, so a
+// unit never straddles a 32-row group and the group's skew moves it as a whole.
+__device__ __forceinline__ unsigned int stage_chunk(uint32_t* buf, const uint32_t* __restrict__ pool,
+                                                    const unsigned int* __restrict__ chunk_count, unsigned int c,
+                                                    unsigned int rw) {
+  const unsigned int cnt = min(chunk_count[c], MCD_CHUNK_ROWS);
+  const uint32_t* cbase = pool + (size_t)c * MCD_CHUNK_ROWS * (size_t)rw;
+  const unsigned int nunits = (cnt * rw + 3u) >> 2;          // (a partial last unit reads inside the chunk's capacity)
+  const unsigned int upg = 8u * rw;                          // units per 32-row group
+  for (unsigned int u = threadIdx.x; u < nunits; u += 256u)
+    cp_async16(buf + 4u * u + kStageSkew * (u / upg), cbase + 4u * u);
+  cp_async_commit();
+  return cnt;
+}
+
+// COLS = true: the payload words 2.. of every row go to one float column each (column j = word 2+j at byte offset
+// j * col_stride) and the channel index to a byte column.  Words 0/1 (electron id, event index) are NOT stored: in
+// trajectory order they follow from the offsets.
+// Double-buffered: while the block scatters chunk k out of one shared-memory buffer, the asynchronous copies of its
+// next chunk fill the other one.
 template <bool COLS>
 __global__ void __launch_bounds__(256) scatter_chunks(const uint32_t* __restrict__ pool,
                                                       const unsigned int* __restrict__ chunk_count, unsigned int nchunks,
@@ -766,7 +798,7 @@ __global__ void __launch_bounds__(256) scatter_chunks(const uint32_t* __restrict
                                                       unsigned char* __restrict__ out, unsigned long long col_stride,
                                                       unsigned long long max_rows,
                                                       const unsigned int* __restrict__ nchunks_dev) {
-  extern __shared__ uint32_t s_rows[];                     // MCD_CHUNK_ROWS * row_words + 32 words
+  extern __shared__ __align__(16) uint32_t s_rows[];       // 2 buffers of stage_words(row_words)
   // max_rows: a run that dropped rows (pool overflow; the caller re-runs it) has event counts beyond the stored
   // rows -- such targets are skipped instead of written past the output
   // enqueued right behind the trajectory kernel (no host round trip): the number of used chunks is still on the device
@@ -775,20 +807,26 @@ __global__ void __launch_bounds__(256) scatter_chunks(const uint32_t* __restrict
   uint32_t* sorted = reinterpret_cast<uint32_t*>(out);
   const unsigned int lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const unsigned int rw = (unsigned int)row_words;
-  for (unsigned int c = blockIdx.x; c < nchunks; c += gridDim.x) {
-    const unsigned int cnt = min(chunk_count[c], MCD_CHUNK_ROWS);
-    const uint32_t* cbase = pool + (size_t)c * MCD_CHUNK_ROWS * (size_t)row_words;
-    const unsigned int nwords = cnt * rw;
-    __syncthreads();                                       // (the previous chunk has been consumed)
-    for (unsigned int k = threadIdx.x; k < nwords; k += 256u) {
-      const unsigned int i = k / rw;
-      s_rows[k + (i >> 5)] = __ldcs(cbase + k);
+  const unsigned int bufw = stage_words(rw);
+  unsigned int c = blockIdx.x;
+  if (c >= nchunks) return;
+  unsigned int b = 0u;
+  unsigned int cnt = stage_chunk(s_rows, pool, chunk_count, c, rw);
+  while (true) {
+    const unsigned int cn = c + gridDim.x;
+    unsigned int cnt_next = 0u;
+    if (cn < nchunks) {
+      cnt_next = stage_chunk(s_rows + (b ^ 1u) * bufw, pool, chunk_count, cn, rw);
+      cp_async_wait<1>();                                  // chunk c has landed, chunk cn is in flight
+    } else {
+      cp_async_wait<0>();
     }
     __syncthreads();
+    const uint32_t* buf = s_rows + b * bufw;
     for (unsigned int r = warp; r < 32u; r += 8u) {
       const unsigned int i = lane * 32u + r;
       if (i >= cnt) continue;
-      const uint32_t* src = s_rows + i * rw + (i >> 5);
+      const uint32_t* src = buf + i * rw + kStageSkew * lane;          // (i >> 5 == lane)
       const uint32_t rel = src[0], w1 = src[1];
       const unsigned long long d = offsets[rel] + (unsigned long long)(w1 & 0xffffffu);
       if (d >= max_rows) continue;
@@ -801,6 +839,11 @@ __global__ void __launch_bounds__(256) scatter_chunks(const uint32_t* __restrict
         for (unsigned int w = 0; w < rw; ++w) dst[w] = src[w];
       }
     }
+    if (cn >= nchunks) break;
+    __syncthreads();                                       // buffer b may be refilled in the next round
+    c = cn;
+    cnt = cnt_next;
+    b ^= 1u;
   }
 }
 
@@ -818,7 +861,7 @@ cudaError_t mcd_launch_order_scats(const unsigned int* nev, unsigned long long c
   scan_apply<<<ntiles, kScanT, 0, stream>>>(nev, count, tile_tmp, offsets);
   if (sorted && nchunks) {
     const unsigned int grid = nchunks < (unsigned int)(sm_count * 64) ? nchunks : (unsigned int)(sm_count * 64);
-    const size_t smem = ((size_t)MCD_CHUNK_ROWS * (size_t)row_words + 32) * sizeof(uint32_t);     // 24.1 .. 56.1 KB
+    const size_t smem = 2 * (size_t)stage_words((unsigned int)row_words) * sizeof(uint32_t);      // 25 .. 116 KB
     auto kern = col_stride ? scatter_chunks<true> : scatter_chunks<false>;
     if (smem > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -866,7 +909,9 @@ int mcd_traj_uses_queue(const DevParams& P, bool scats) {
 }
 
 cudaError_t mcd_launch_traj(const DevParams& P, const DevOut& O_in, unsigned long long first_id,
-                            unsigned long long count, int sm_count, cudaStream_t stream, TrajLaunchInfo* info) {
+                            unsigned long long count, int sm_count, cudaStream_t stream_in, TrajLaunchInfo* info,
+                            const TrajTailStream* tail) {
+  cudaStream_t stream = stream_in;
   const bool scats = (P.scat_row_words > 0) && (O_in.scats != nullptr);
   TrajKernel k = pick_kernel(P, scats);
   if (!k) return cudaErrorInvalidValue;
@@ -895,6 +940,15 @@ cudaError_t mcd_launch_traj(const DevParams& P, const DevOut& O_in, unsigned lon
     O.dump_T = last ? -1 : dump_T;
     if (p == 0) {
       k<<<li.blocks, li.threads, 0, stream>>>(P, O, first_id, count);
+      // Several runs in flight on several streams: the hand-over passes of THIS run become eligible only when its
+      // first pass ends, by which time the first passes of the runs launched after it are already waiting for SM
+      // slots and would be served first.  On a high-priority side stream the (short, sparse) tail of a run gets the
+      // next free slots instead, so a run completes one main pass after it started rather than `depth` of them.
+      if (passes > 1 && tail && tail->stream && P.tune_tail_priority) {
+        if ((err = cudaEventRecord(tail->first_done, stream)) != cudaSuccess) return err;
+        if ((err = cudaStreamWaitEvent(tail->stream, tail->first_done, 0)) != cudaSuccess) return err;
+        stream = tail->stream;
+      }
     } else {
       TrajKernel kr = pick_kernel_pool<true>(P);
       // same shared-memory carve-out as the first pass
@@ -917,6 +971,10 @@ cudaError_t mcd_launch_traj(const DevParams& P, const DevOut& O_in, unsigned lon
     hist_kernel<<<(unsigned int)(nb ? nb : 1), 256, 0, stream>>>(P.hist, O_in.els, count, O_in.stats);
     err = cudaGetLastError();
     if (err != cudaSuccess) return err;
+  }
+  if (stream != stream_in) {                               // back to the caller's stream
+    if ((err = cudaEventRecord(tail->tail_done, stream)) != cudaSuccess) return err;
+    if ((err = cudaStreamWaitEvent(stream_in, tail->tail_done, 0)) != cudaSuccess) return err;
   }
   return cudaSuccess;
 }

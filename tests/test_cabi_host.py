@@ -38,7 +38,7 @@ def test_struct_sizes_match_header(lib):
     assert C.sizeof(_lib.Material) == 8 + 6 * 8 + 2 * 8 * 8
     assert C.sizeof(_lib.Params) == 7 * 8 + 8 + 4 * 4 + 4 * 4 + 8
     assert _lib.EL_ROW_DTYPE.itemsize == 32
-    assert C.sizeof(_lib.Tuning) == 16
+    assert C.sizeof(_lib.Tuning) == 20
     assert C.sizeof(_lib.Counters) == 8 * (2 + 5 + 5 + 11)
 
 

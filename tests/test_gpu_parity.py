@@ -894,7 +894,7 @@ def test_launch_tuning_never_changes_a_result():
     g = golden_tables('Si_15k_small')
     ref = None
     for kw in ({}, dict(handover_passes=1), dict(handover_passes=2, handover_threshold=8), dict(blocks_per_sm=2),
-               dict(statistics_kernel=1), dict(handover_passes=4, handover_threshold=31, blocks_per_sm=1)):
+               dict(statistics_kernel=1), dict(tail_priority=0), dict(handover_passes=4, handover_threshold=31, blocks_per_sm=1)):
         eng = make_engine(scatter_output=[])
         t = eng.tuning(**kw)
         for k, v in kw.items():
@@ -908,7 +908,7 @@ def test_launch_tuning_never_changes_a_result():
         cur = (res.els.tobytes(), eng.stats_host().tobytes())
         if ref is None:
             ref = cur
-            assert t == dict(handover_passes=3, handover_threshold=31, blocks_per_sm=0, statistics_kernel=0)
+            assert t == dict(handover_passes=3, handover_threshold=31, blocks_per_sm=0, statistics_kernel=0, tail_priority=1)
             with pytest.raises(MCDError):
                 eng.tuning(handover_passes=2)              # after set_capacity
         assert cur == ref, kw
