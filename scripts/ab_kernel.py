@@ -28,6 +28,8 @@ def child(a):
     ip = dict(maxScatt=1000, thickness=3e6, Wc=10., tol_E=1e-4, tol_W=1e-7,
               electron_output=['outcome', 'final_E', 'final_dir', 'last_pos'], scatter_output=[], seed=12345)
     ip.update(WL[a.workload])
+    if a.tol:
+        ip['tol_E'], ip['tol_W'] = [float(x) for x in a.tol.split(',')]
     eng = Engine(ip, device=0)
     if ip['mode'] == 'DS':
         genTables(ip, engine=eng)
@@ -78,6 +80,7 @@ def child(a):
 
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument('--tol', default='', help='tol_E,tol_W (default: BASELINE defaults 1e-4,1e-7)')
     ap.add_argument('--workload', default='C2')
     ap.add_argument('--n', type=int, default=1000000)
     ap.add_argument('--reps', type=int, default=8)
@@ -95,7 +98,7 @@ def main():
         else:
             env.update(dict(kv.split('=', 1) for kv in var.split(',')))
         cmd = [sys.executable, os.path.abspath(__file__), '--child', '--workload', a.workload, '--n', str(a.n),
-               '--reps', str(a.reps), '--tag', var, '--pipes', ','.join(map(str, a.pipes))]
+               '--reps', str(a.reps), '--tag', var, '--pipes', ','.join(map(str, a.pipes))] + (['--tol', a.tol] if a.tol else [])
         try:      # a variant that hangs must not eat the GPU budget
             r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=120)
             sys.stdout.write(r.stdout if r.returncode == 0 else 'FAILED %s\n%s\n' % (var, r.stderr[-2000:]))

@@ -1,6 +1,8 @@
 """Statistical parity report at larger sizes than the test-suite uses: GPU (2e6 electrons) vs the float64 C oracle
 (2e5 electrons, INDEPENDENT Philox seed) on the same tables; plus same-seed agreement on 1e5 electrons.
-Writes one JSON line per configuration (profiles/r1_statistics.jsonl)."""
+Writes one JSON line per configuration (profiles/r1_statistics.jsonl).
+--default-tol: BASELINE's default tolerances (tol_E 1e-4, tol_W 1e-7); the GPU runs on tables BUILT ON THE DEVICE, the
+oracle on its own tables (about 30 s of numpy per material)."""
 import json, math, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'oracle'))
@@ -16,13 +18,20 @@ CFG = [('C2 Si 20keV DS 70deg', dict(material='Si', E0=20000., Emin=10000., s_ti
        ('C5 Cu 15keV cont-JL 70deg', dict(material='Cu', E0=15000., Emin=750., s_tilt=70., mode='cont', Bethe_model='JL', maxScatt=100000)),
        ('C5 Au 10keV cont-explicit 70deg', dict(material='Au', E0=10000., Emin=500., s_tilt=70., mode='cont', Bethe_model='explicit', maxScatt=100000))]
 NT = os.cpu_count() or 1
+DEFAULT_TOL = '--default-tol' in sys.argv
 for tag, kw in CFG:
     ip = dict(thickness=3e6, Wc=10., tol_E=1e-3, tol_W=1e-4, Bethe_model='classical', seed=20261017,
               electron_output=['outcome', 'final_E', 'final_dir', 'last_pos'], scatter_output=[])
     ip.update(kw)
+    if DEFAULT_TOL:
+        ip.update(tol_E=1e-4, tol_W=1e-7)
     tabs = o.gen_tables(ip, strict=False) if ip['mode'] == 'DS' else None
     eng = Engine(ip, device=0)
-    if tabs:
+    if tabs and DEFAULT_TOL:
+        from mcdiscrete_b200.probTables import genTables
+        dt = genTables(ip, engine=eng)
+        assert np.array_equal(dt['Moller'].Es, tabs['Moller'].Es) and np.array_equal(dt['Gryz'][0].Ws, tabs['Gryz'][0].Ws)
+    elif tabs:
         eng.table_upload(0, tabs['Moller'].Es, tabs['Moller'].Ws, tabs['Moller'].table)
         eng.table_upload(1, tabs['Gryz'][0].Es, tabs['Gryz'][0].Ws, tabs['Gryz'][0].table)
         eng.tables = tabs
@@ -45,7 +54,7 @@ for tag, kw in CFG:
         'depth_last_z': stats.ks_2samp(res.els['last_z'][b].astype(np.float64), ref['last_pos'][rb, 2]).pvalue,
         'abs_last_z': stats.ks_2samp(res.els['last_z'][out == 0].astype(np.float64), ref['last_pos'][ref['outcome'] == 0, 2]).pvalue,
     }
-    print(json.dumps(dict(config=tag, n_gpu=n_gpu, n_oracle=n_ref, eta_gpu=float(eg), eta_oracle=float(er), eta_diff_in_sigma=float((eg - er) / sig),
+    print(json.dumps(dict(config=tag, tol_E=ip['tol_E'], tol_W=ip['tol_W'], tables='device-built vs oracle-built' if (tabs and DEFAULT_TOL) else 'oracle-built, uploaded', n_gpu=n_gpu, n_oracle=n_ref, eta_gpu=float(eg), eta_oracle=float(er), eta_diff_in_sigma=float((eg - er) / sig),
                           ks_p={k: float(v) for k, v in ks.items()}, events_per_electron_gpu=res.counters['events'] / n_gpu,
                           events_per_electron_oracle=float(ref['n_ev'].mean()),
                           same_seed_outcome_agreement=float((out[:100000] == same['outcome']).mean()),
