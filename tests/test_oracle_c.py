@@ -112,3 +112,52 @@ def test_c_port_threads_and_q4():
     assert np.array_equal(a['outcome'], g['outcome'][first])
     assert np.array_equal(a['n_rows'], g['n_els'])
     assert np.array_equal(a['n_ev'], g['n_ev'])
+
+
+# ---- the reference's OWN random numbers: tests/golden/stats_*.npz are samples of the unmodified reference run with
+# `random.seed(SEED + id)` per electron (oracle/gen_golden_stats.py), no Philox injection anywhere.  The C port (the
+# statistical oracle of the GPU tests) must draw from the same distributions. ---------------------------------------
+STAT_CASES = [('DS_Si', {}, 'Si_15k_small'), ('DS_Cu', dict(material='Cu', Emin=10000.), 'Cu_10k_small'),
+              ('cont_Al', dict(material='Al', Emin=500., mode='cont', Bethe_model='classical', maxScatt=100000), None)]
+
+
+def reference_sample_checks(sample, ref, n_sample):
+    """Backscatter coefficient within 3 sigma, two-sample KS (p > 0.001: fifteen tests in the family) on final
+    energy / exit polar angle / azimuth / last depth of the backscattered and last depth of the absorbed electrons,
+    mean trajectory length within 4 standard errors.  `sample`, `ref`: dicts with outcome, final_E, final_dir,
+    last_pos, n_ev."""
+    from scipy import stats
+    n_ref = len(ref['outcome'])
+    eg, er = (sample['outcome'] == 1).mean(), (ref['outcome'] == 1).mean()
+    sd = np.sqrt(eg * (1 - eg) / n_sample + er * (1 - er) / n_ref)
+    assert abs(eg - er) < 3 * sd, (eg, er, sd)
+    b, rb = sample['outcome'] == 1, ref['outcome'] == 1
+    rng = np.random.default_rng(0)
+    jit = lambda x: np.asarray(x, np.float64) + rng.uniform(-0.05, 0.05, len(x))      # breaks the ties of the energy comb
+    f64 = lambda x: np.asarray(x, np.float64)
+    pairs = {
+        'final_E': (jit(sample['final_E'][b]), jit(ref['final_E'][rb])),
+        'exit_polar': (np.arccos(np.clip(-f64(sample['final_dir'][b, 2]), -1, 1)), np.arccos(np.clip(-f64(ref['final_dir'][rb, 2]), -1, 1))),
+        'exit_azimuth': (np.arctan2(f64(sample['final_dir'][b, 1]), f64(sample['final_dir'][b, 0])),
+                         np.arctan2(f64(ref['final_dir'][rb, 1]), f64(ref['final_dir'][rb, 0]))),
+        'depth_last_z': (f64(sample['last_pos'][b, 2]), f64(ref['last_pos'][rb, 2])),
+        'abs_last_z': (f64(sample['last_pos'][sample['outcome'] == 0, 2]), f64(ref['last_pos'][ref['outcome'] == 0, 2])),
+    }
+    ps = {k: float(stats.ks_2samp(a, c).pvalue) for k, (a, c) in pairs.items() if len(a) >= 50 and len(c) >= 50}
+    se = ref['n_ev'].std() / np.sqrt(n_ref)
+    print('eta %.4f vs reference %.4f (sd %.4f); KS p %s; mean events %.2f vs %.2f (se %.2f)'
+          % (eg, er, sd, {k: '%.3g' % v for k, v in ps.items()}, sample['n_ev'].mean(), ref['n_ev'].mean(), se))
+    assert all(v > 1e-3 for v in ps.values()), ps
+    assert abs(sample['n_ev'].mean() - ref['n_ev'].mean()) < 4 * se
+    return ps
+
+
+@pytest.mark.parametrize('tag,kw,tkey', STAT_CASES)
+def test_c_port_draws_from_the_reference_distributions(tag, kw, tkey):
+    ref = dict(np.load(os.path.join(GOLD, 'stats_%s.npz' % tag)))
+    ip = dict(E0=20000., Emin=15000., material='Si', s_tilt=70., thickness=3e6, mode='DS', maxScatt=1000, Wc=10.)
+    ip.update(kw)
+    n = 60000
+    c = oc.run(ip, 0, n, 31337, _golden_tabs(tkey) if tkey else None, nthreads=os.cpu_count() or 1)
+    assert len(ref['outcome']) >= 4000 and int(ref['double_records'].max()) <= 1
+    reference_sample_checks(c, ref, n)
