@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY.  STATISTICAL golden samples from the reference's own, unmodified code WITH ITS OWN RNG
 (`random`, Mersenne Twister), in the build container:
 
-    python oracle/gen_golden_stats.py [n_DS n_cont]      # writes tests/golden/stats_*.npz (default 8000 / 6000 electrons; float32 is enough for the distributions)
+    python oracle/gen_golden_stats.py [n_DS n_cont [config ...]]      # writes tests/golden/stats_*.npz (default 8000 / 6000 electrons; float32 is enough for the distributions)
 
 The other golden files replace `random.random` by Philox streams so that single trajectories can be compared event
 for event.  These samples do not: every electron is `random.seed(SEED + id)` followed by the reference's
@@ -80,7 +80,18 @@ def main():
 
     cfgs = [('DS_Si', gg.base_input(), n_ds, 'Si_15k_small'),
             ('DS_Cu', gg.base_input(material='Cu', Emin=10000.), n_ds // 2, 'Cu_10k_small'),
-            ('cont_Al', gg.base_input(material='Al', Emin=500., mode='cont', maxScatt=100000), n_cont, None)]
+            ('cont_Al', gg.base_input(material='Al', Emin=500., mode='cont', maxScatt=100000), n_cont, None),
+            # a 9000 Angstrom film at normal incidence ('trsm' outcomes, electron.py:73-81) and the Mott elastic channel
+            # on the synthetic ioffe-layout table of oracle/gen_golden_mott.py
+            ('DS_Si_thin', gg.base_input(thickness=9000., s_tilt=0.), n_ds // 2, 'Si_15k_small'),
+            ('DS_Si_mott', gg.base_input(elastic='Mott'), n_ds // 2, 'Si_15k_small')]
+    only = [a for a in sys.argv[3:]]
+    if only:
+        cfgs = [c for c in cfgs if c[0] in only]
+    import shutil
+    work_mott = os.path.abspath(os.path.join('..', 'tables', 'mott', 'ioffe'))
+    os.makedirs(work_mott, exist_ok=True)
+    shutil.copy(os.path.join(os.path.dirname(HERE), 'tests', 'data', 'tables', 'mott', 'ioffe', 'Si.ioffe'), work_mott)
     for tag, ip, n, tkey in cfgs:
         tb = None
         if tkey:

@@ -421,18 +421,26 @@ def test_watson_two_sample_tests_of_the_reference():
 # random.seed(SEED + id) per electron, oracle/gen_golden_stats.py): the CUDA path as an independent sample ------------
 @pytest.mark.parametrize('tag,kw,tkey', [('DS_Si', {}, 'Si_15k_small'), ('DS_Cu', dict(material='Cu', Emin=10000.), 'Cu_10k_small'),
                                          ('cont_Al', dict(material='Al', Emin=500., mode='cont', Bethe_model='classical',
-                                                          maxScatt=100000), None)])
+                                                          maxScatt=100000), None),
+                                         ('DS_Si_thin', dict(thickness=9000., s_tilt=0.), 'Si_15k_small'),
+                                         ('DS_Si_mott', dict(elastic='Mott'), 'Si_15k_small')])
 def test_gpu_draws_from_the_reference_distributions(tag, kw, tkey):
     from test_oracle_c import reference_sample_checks, _golden_tabs
     ref = dict(np.load(os.path.join(GOLD, 'stats_%s.npz' % tag)))
     ip = dict(E0=20000., Emin=15000., material='Si', s_tilt=70., thickness=3e6, mode='DS', maxScatt=1000, Wc=10.,
               electron_output=['outcome', 'final_E', 'final_dir', 'last_pos'], scatter_output=[], seed=424242)
     ip.update(kw)
-    eng = _engine(ip, _golden_tabs(tkey) if tkey else None)
+    def engine(ipx):
+        e = _engine(ipx, _golden_tabs(tkey) if tkey else None)
+        if ipx.get('elastic') == 'Mott':
+            from mcdiscrete_b200.extFunctions import mottTable
+            mottTable(14, 'Si', os.path.join(os.path.dirname(__file__), 'data', 'tables', 'mott') + os.sep).upload(e)
+        return e
+    eng = engine(ip)
     n = 400000
     res = eng.run(count=n, first_id=0, ordered=False)
     # trajectory lengths: the per-electron event counts of a second, row-recording run of the first 40000 ids
-    eng2 = _engine(dict(ip, scatter_output=['energy']), _golden_tabs(tkey) if tkey else None)
+    eng2 = engine(dict(ip, scatter_output=['energy']))
     r2 = eng2.run(count=40000, first_id=0, ordered='columns')
     nev = np.diff(r2.scats.offsets.astype(np.int64))
     sample = dict(outcome=res.outcome, final_E=res.els['final_E'],

@@ -118,7 +118,8 @@ def test_c_port_threads_and_q4():
 # `random.seed(SEED + id)` per electron (oracle/gen_golden_stats.py), no Philox injection anywhere.  The C port (the
 # statistical oracle of the GPU tests) must draw from the same distributions. ---------------------------------------
 STAT_CASES = [('DS_Si', {}, 'Si_15k_small'), ('DS_Cu', dict(material='Cu', Emin=10000.), 'Cu_10k_small'),
-              ('cont_Al', dict(material='Al', Emin=500., mode='cont', Bethe_model='classical', maxScatt=100000), None)]
+              ('cont_Al', dict(material='Al', Emin=500., mode='cont', Bethe_model='classical', maxScatt=100000), None),
+              ('DS_Si_thin', dict(thickness=9000., s_tilt=0.), 'Si_15k_small')]       # 'trsm' outcomes
 
 
 def reference_sample_checks(sample, ref, n_sample):
@@ -131,6 +132,9 @@ def reference_sample_checks(sample, ref, n_sample):
     eg, er = (sample['outcome'] == 1).mean(), (ref['outcome'] == 1).mean()
     sd = np.sqrt(eg * (1 - eg) / n_sample + er * (1 - er) / n_ref)
     assert abs(eg - er) < 3 * sd, (eg, er, sd)
+    for code in (0, 2, 4):                                   # abs, trsm, long fractions too
+        fg, fr = (sample['outcome'] == code).mean(), (ref['outcome'] == code).mean()
+        assert abs(fg - fr) <= 3 * np.sqrt(fg * (1 - fg) / n_sample + fr * (1 - fr) / n_ref) + 1e-12, (code, fg, fr)
     b, rb = sample['outcome'] == 1, ref['outcome'] == 1
     rng = np.random.default_rng(0)
     jit = lambda x: np.asarray(x, np.float64) + rng.uniform(-0.05, 0.05, len(x))      # breaks the ties of the energy comb
@@ -142,6 +146,9 @@ def reference_sample_checks(sample, ref, n_sample):
                          np.arctan2(f64(ref['final_dir'][rb, 1]), f64(ref['final_dir'][rb, 0]))),
         'depth_last_z': (f64(sample['last_pos'][b, 2]), f64(ref['last_pos'][rb, 2])),
         'abs_last_z': (f64(sample['last_pos'][sample['outcome'] == 0, 2]), f64(ref['last_pos'][ref['outcome'] == 0, 2])),
+        'trsm_final_E': (jit(sample['final_E'][sample['outcome'] == 2]), jit(ref['final_E'][ref['outcome'] == 2])),
+        'trsm_exit_polar': (np.arccos(np.clip(f64(sample['final_dir'][sample['outcome'] == 2, 2]), -1, 1)),
+                            np.arccos(np.clip(f64(ref['final_dir'][ref['outcome'] == 2, 2]), -1, 1))),
     }
     ps = {k: float(stats.ks_2samp(a, c).pvalue) for k, (a, c) in pairs.items() if len(a) >= 50 and len(c) >= 50}
     se = ref['n_ev'].std() / np.sqrt(n_ref)
@@ -161,3 +168,18 @@ def test_c_port_draws_from_the_reference_distributions(tag, kw, tkey):
     c = oc.run(ip, 0, n, 31337, _golden_tabs(tkey) if tkey else None, nthreads=os.cpu_count() or 1)
     assert len(ref['outcome']) >= 4000 and int(ref['double_records'].max()) <= 1
     reference_sample_checks(c, ref, n)
+
+
+def test_python_port_mott_draws_from_the_reference_distribution():
+    """elastic = 'Mott' (synthetic ioffe-layout table): the Python port against the reference's own-RNG sample (the C
+    port has no Mott channel; the GPU test compares the CUDA path with the same sample)."""
+    ref = dict(np.load(os.path.join(GOLD, 'stats_DS_Si_mott.npz')))
+    ip = dict(E0=20000., Emin=15000., material='Si', s_tilt=70., thickness=3e6, mode='DS', maxScatt=1000, Wc=10., elastic='Mott')
+    tabs = _golden_tabs('Si_15k_small')
+    tabs['Mott'] = o.MottTable(14, 'Si', os.path.join(os.path.dirname(__file__), 'data', 'tables', 'mott') + os.sep).read_ioffe().to_prob_table()
+    n = 1500
+    els = o.run_electrons(ip, 0, n, 777, tabs)
+    sample = dict(outcome=np.array([o.OUTCOMES.index(e.els[0][0]) for e in els]), final_E=np.array([e.els[0][1] for e in els]),
+                  final_dir=np.array([e.els[0][2] for e in els]), last_pos=np.array([e.els[0][3] for e in els]),
+                  n_ev=np.array([len(e.scats) for e in els]))
+    reference_sample_checks(sample, ref, n)
