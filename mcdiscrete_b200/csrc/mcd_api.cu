@@ -374,8 +374,6 @@ void build_dev_params(mcd_ctx* c) {
     m.gE[k] = on ? (float)mt.shell_E[i] : 3.0e38f;                 // unused slots: never ionisable
     m.gInvE[k] = on ? (float)(1.0 / mt.shell_E[i]) : 0.f;
     m.gC[k] = on ? (float)(mt.shell_n[i] * kPiEFour * scale / mt.shell_E[i]) : 0.f;
-    m.sN[k] = on ? (float)mt.shell_n[k] : 0.f;
-    m.sInvE[k] = on ? (float)(1.0 / mt.shell_E[k]) : 1.f;
   }
   const double J = (mt.Z >= 13) ? (9.76 * Z + 58.5 / pow(Z, 0.19)) : 11.5 * Z;   // stoppingPowers.py:134-137
   m.spC = (float)(2.0 * kPiEFour * mt.atnd * 1e-14);
@@ -384,6 +382,14 @@ void build_dev_params(mcd_ctx* c) {
   m.kJ = (float)(mt.bethe_k * J);
   m.n_val = (float)mt.n_val;
   m.inv_Eval = (float)(1.0 / mt.E_val);
+  {
+    double N = mt.n_val, C = mt.n_val * log(mt.E_val);
+    for (int i = 0; i < mt.n_shells; ++i) { N += mt.shell_n[i]; C += mt.shell_n[i] * log(mt.shell_E[i]); }
+    const double inv = exp(-C / N);
+    m.spN = (float)N;
+    m.inv_Eeff_hi = (float)inv;
+    m.inv_Eeff_lo = (float)(inv - (double)m.inv_Eeff_hi);
+  }
 
   P.E0 = (float)p.E0;
   P.Emin = (float)p.Emin;

@@ -18,6 +18,7 @@ WL = {
     'cont': dict(material='Al', E0=20000., Emin=500., mode='continuous', Bethe_model='classical', s_tilt=70.),
     'contJL': dict(material='Al', E0=20000., Emin=500., mode='continuous', Bethe_model='JL', s_tilt=70.),
     'contEx': dict(material='Cu', E0=20000., Emin=500., mode='continuous', Bethe_model='explicit', s_tilt=70.),
+    'contAuEx': dict(material='Au', E0=30000., Emin=1500., mode='continuous', Bethe_model='explicit', s_tilt=70., maxScatt=100000),
 }
 
 
