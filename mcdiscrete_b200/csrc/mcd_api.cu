@@ -377,8 +377,8 @@ void build_dev_params(mcd_ctx* c) {
   }
   const double J = (mt.Z >= 13) ? (9.76 * Z + 58.5 / pow(Z, 0.19)) : 11.5 * Z;   // stoppingPowers.py:134-137
   m.spC = (float)(2.0 * kPiEFour * mt.atnd * 1e-14);
-  m.Zf = (float)Z;
-  m.J = (float)J;
+  m.spCZ = (float)(2.0 * kPiEFour * mt.atnd * 1e-14 * Z);
+  m.cJ = (float)(1.166 / J);
   m.kJ = (float)(mt.bethe_k * J);
   m.n_val = (float)mt.n_val;
   m.inv_Eval = (float)(1.0 / mt.E_val);

@@ -148,7 +148,7 @@ __global__ void k_rotate(const float* d, const float* y, const float* c2, const 
 __global__ void k_stopping(const __grid_constant__ DevParams P, int bethe, const float* E, uint64_t n, float* sp) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  sp[i] = sp_bethe(P.m, bethe, E[i]);
+  sp[i] = sp_bethe(P.m, bethe, E[i], f_rcp(E[i]));
 }
 
 __global__ void k_lookup(const __grid_constant__ DevParams P, int slot, const float* E, const float* u, uint64_t n,
