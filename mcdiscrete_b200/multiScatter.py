@@ -68,6 +68,9 @@ def _engine_for(inputPar, material, thingsToSave, tables=None):
                 for slot, T in enumerate([tables['Moller'], tables['Gryz'][0]]):
                     eng.table_upload(slot, T.Es, T.Ws, np.ma.filled(T.table, 0))
                 eng.tables = tables
+            if tables and tables.get('Mott') is not None and inputPar.get('elastic') == 'Mott':
+                M = tables['Mott']              # ours or the reference's mottTable (extFunctions.py:21-153)
+                eng.mott_upload(M.Es, M.sigmas, np.asarray(M.probTable, dtype=np.float64), M.thetas)
         _engines[key] = eng
     return eng
 

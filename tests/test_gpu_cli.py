@@ -279,3 +279,46 @@ def test_non_uniform_energy_axis_is_bisected():
         eng.table_upload(0, bad, g['moller_Ws'], g['moller_table'])
     assert ei.value.code == -1
     eng.close()
+
+
+def test_mott_through_the_worker_and_the_command_line(tmp_path):
+    """elastic: Mott end to end: genTables reads the ioffe-layout table and uploads it, multiTraj_DS labels the
+    elastic channel 'Mott' (scattering.py:589) -- on the engine the tables were built on and on a fresh engine made
+    for other output columns -- and the doScatter-style command line writes the label into the store."""
+    from mcdiscrete_b200 import material, genTables, multiTraj_DS
+    from mcdiscrete_b200.store import read_store
+    mott_path = os.path.join(os.path.dirname(__file__), 'data', 'tables', 'mott') + os.sep
+    ip = dict(num_el=40, E0=20000., Emin=15000., material='Si', s_tilt=70., thickness=3e6, elastic='Mott',
+              mode='DS', Bethe_model='classical', diffMFP=False, gen_tables=True, tol_E=1e-2, tol_W=1e-3,
+              maxScatt=1000, Wc=10., electron_output=['outcome', 'final_E'], scatter_output=['type', 'pol_angle'],
+              mott_path=mott_path)
+    tables = genTables(ip)
+    assert set(tables) == {'Moller', 'Gryz', 'Mott'} and tables['Mott'].probTable.shape == (56, 101)
+    what = {'el_output': ip['electron_output'], 'scat_output': ip['scatter_output']}
+    res = multiTraj_DS(ip, 40, material('Si'), tables, what)
+    types = [t for r in res for t in r['scats']['type']]
+    assert 'Mott' in types and 'Ruth' not in types and set(types) <= {'Mott', 'Moller', 'Quinn', 'Gryz1s', 'Gryz2s', 'Gryz2p'}
+    pol = np.array([c for r in res for t, c in zip(r['scats']['type'], r['scats']['pol_angle']) if t == 'Mott'])
+    grid = np.cos(np.radians(tables['Mott'].thetas * 0.5)) ** 2
+    assert np.abs(pol[:, None] - grid[None, :]).min(axis=1).max() < 1e-6        # only angles of the table's grid
+    what2 = {'el_output': ['outcome'], 'scat_output': ['type', 'energy']}       # another context: tables are moved over
+    res2 = multiTraj_DS(ip, 10, material('Si'), tables, what2)
+    assert any(t == 'Mott' for r in res2 for t in r['scats']['type'])
+    # command line, run from a directory next to tables/ like the reference ('../tables/mott/', extFunctions.py:44)
+    import shutil
+    shutil.copytree(os.path.join(os.path.dirname(__file__), 'data', 'tables', 'mott'), tmp_path / 'tables' / 'mott')
+    os.makedirs(tmp_path / 'run', exist_ok=True)
+    inp = tmp_path / 'input.file'
+    inp.write_text('\n'.join([
+        'num_el : 300', 'E0 : 20000 # eV', 'Emin : 15000', 'material : Si', 's_tilt : 70', 'thickness : 3000000',
+        'elastic : Mott # Mott or Ruth_vanilla', 'mode : DS', 'Bethe_model : classical', 'diffMFP : no', 'gen_tables : yes',
+        'tol_E : 1e-2', 'tol_W : 1e-3', 'maxScatt: 1000', 'Wc : 10',
+        'electron_output : outcome, final_E', 'scatter_output : type, energy']))
+    out = str(tmp_path / 'mott.h5')
+    r = subprocess.run([sys.executable, '-m', 'mcdiscrete_b200', '-i', str(inp), '-o', out], cwd=str(tmp_path / 'run'),
+                       env=dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get('PYTHONPATH', '')),
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    back = read_store(out)
+    assert len(back['els']) == 300
+    assert 'Mott' in set(x.decode() if isinstance(x, bytes) else str(x) for x in back['scats']['type'].unique())
