@@ -37,7 +37,13 @@ typedef struct {
   unsigned long long seed;
   int elastic; /* sigma evaluated for the elastic channel: 0 ruther_sigma, 1 ruther_sigma_wDefl, 2 ruther_N_sigma,
                   3 ruther_N_sigma_wDefl (the label -> function mapping of scattering.py:483-491 / :781-789 is done
-                  by the caller, oracle/mcd_oracle.py::elastic_sigma) */
+                  by the caller, oracle/mcd_oracle.py::elastic_sigma); 4 = 'Mott' (DS only): sigma and polar angle from
+                  the table below (scattering.py:493, :588-591, :96-122) */
+  int mott_nE, mott_nT;
+  const double* mott_Es;    /* nE ascending (extFunctions.py:93-97) */
+  const double* mott_sig;   /* nE, cm^2 */
+  const double* mott_cdf;   /* nE x nT (probTable, extFunctions.py:99-109) */
+  const double* mott_theta; /* nT, degrees */
 } orc_par;
 
 static const double PI_EFOUR = 6.51408491409531e-14; /* parameters.py:7 */
@@ -65,6 +71,14 @@ static double elastic_sigma(int kind, double E, double Z) {
   if (kind == 1) return ruther_sigma(E, Z) / (Z * Z) * (Z * (Z + 1.));                       /* :63-84 */
   double b = 0.48 * (5.43 * pow(Z, 2. / 3.) / E);                                             /* :89-143 */
   return PI_EFOUR * (kind == 2 ? Z * Z : (Z + 1.) * Z) / (4 * b * (1 + b) * (E * E));
+}
+static int bisect_left_d(const double* a, int n, double x) {       /* bisect.bisect_left on a float64 array */
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) / 2;
+    if (a[mid] < x) lo = mid + 1; else hi = mid;
+  }
+  return lo;
 }
 static double moller_sigma(double E, double Wc, double nfree) {                               /* :183-208 */
   if (E <= Wc) return 0.;
@@ -170,7 +184,8 @@ static void one_electron(const orc_par* p, const orc_mat* m, const orc_tab* tm, 
     double pos0[3] = {xyz[0], xyz[1], xyz[2]};
     if (p->mode == 0) {
       double sig[ORC_MAX_CH], tot = 0.;
-      sig[0] = elastic_sigma(p->elastic, E, m->Z);
+      sig[0] = (p->elastic == 4) ? p->mott_sig[bisect_left_d(p->mott_Es, p->mott_nE, E)]    /* scattering.py:493 */
+                                 : elastic_sigma(p->elastic, E, m->Z);
       sig[1] = moller_sigma(E, p->Wc, m->n_val);
       for (int i = 0; i < m->nshell; ++i) sig[2 + i] = gryz_sigma(E, m->Es[i], m->ns[i]);
       sig[nch - 1] = quinn_sigma(E, m->Epl, m->Ef, m->atnd, m->bohr_r);
@@ -192,7 +207,13 @@ static void one_electron(const orc_par* p, const orc_mat* m, const orc_tab* tm, 
       xyz[0] += pathl * d[0]; xyz[1] += pathl * d[1]; xyz[2] = nz;
     }
     if (p->mode == 0) {
-      if (ch == 0) {                                  /* scattering.py:575-577, :125-152 */
+      if (ch == 0 && p->elastic == 4) {               /* Mott: scattering.py:588-591, pickMottTable :96-122 */
+        W = 0.;
+        const double* row = p->mott_cdf + (size_t)bisect_left_d(p->mott_Es, p->mott_nE, E) * (size_t)p->mott_nT;
+        double theta = p->mott_theta[bisect_left_d(row, p->mott_nT, u2)];
+        double ch2 = cos(theta * 0.5 * (M_PI / 180.0));        /* np.radians */
+        c2 = ch2 * ch2;
+      } else if (ch == 0) {                           /* scattering.py:575-577, :125-152 */
         W = 0.;
         double a = alpha_(E, m->Z);
         c2 = 1. - (a * u2 / (1. + a - u2));
@@ -258,6 +279,7 @@ static void* worker(void* arg) {
 int orc_run(const orc_par* p, const orc_mat* m, const orc_tab* tm, const orc_tab* tg, uint64_t first,
             uint64_t count, double* els, int* nev, int nthreads, double* ev_rows, long max_ev_rows) {
   if (p->mode == 0 && (!tm || !tg)) return -1;
+  if (p->elastic == 4 && (p->mode != 0 || !p->mott_Es || !p->mott_sig || !p->mott_cdf || !p->mott_theta)) return -2;
   if (ev_rows) {
     long cursor = 0;
     for (uint64_t i = 0; i < count; ++i)

@@ -25,7 +25,9 @@ class CTab(C.Structure):
 class CPar(C.Structure):
     _fields_ = [('E0', C.c_double), ('Emin', C.c_double), ('tilt_deg', C.c_double), ('thickness', C.c_double),
                 ('Wc', C.c_double), ('maxScatt', C.c_long), ('mode', C.c_int), ('bethe', C.c_int),
-                ('seed', C.c_ulonglong), ('elastic', C.c_int)]
+                ('seed', C.c_ulonglong), ('elastic', C.c_int), ('mott_nE', C.c_int), ('mott_nT', C.c_int),
+                ('mott_Es', C.POINTER(C.c_double)), ('mott_sig', C.POINTER(C.c_double)),
+                ('mott_cdf', C.POINTER(C.c_double)), ('mott_theta', C.POINTER(C.c_double))]
 
 
 _lib = None
@@ -59,12 +61,22 @@ def run(inputPar, first_id, count, seed, tables=None, mat=None, nthreads=1, even
         m.Es[i], m.ns[i] = e, n
     ds = inputPar['mode'] == 'DS'
     el = inputPar.get('elastic', 'Ruth_vanilla')
+    mott = el == 'Mott'
+    if mott and not ds:
+        raise ValueError("elastic = 'Mott' exists in DS mode only")
     if not ds:                                        # scattering.py:781-789: the _wDefl branches are unreachable
         el = 'Ruth_vanilla' if 'vanilla' in el else 'Ruth_nigram'
     p = CPar(inputPar['E0'], inputPar['Emin'], inputPar['s_tilt'], inputPar['thickness'], inputPar.get('Wc', 10.),
              int(inputPar['maxScatt']), 0 if ds else 1,
              {'classical': 0, 'JL': 1, 'explicit': 2}[inputPar.get('Bethe_model', 'classical')], seed,
-             o.ELASTIC_MODELS.index(el))
+             4 if mott else o.ELASTIC_MODELS.index(el))
+    if mott:
+        M = tables['Mott']
+        keep = [np.ascontiguousarray(a, np.float64) for a in (M.Es, M.sigmas, M.probTable, M.thetas)]
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        p.mott_nE, p.mott_nT = len(keep[0]), len(keep[3])
+        p.mott_Es, p.mott_sig, p.mott_cdf, p.mott_theta = dp(keep[0]), dp(keep[1]), dp(keep[2]), dp(keep[3])
+        p._keep = keep
     tm = _tab(tables['Moller']) if ds else None
     tg = _tab(tables['Gryz'][0]) if ds else None
     els = np.empty((count, 9), np.float64)

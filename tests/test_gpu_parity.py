@@ -851,7 +851,8 @@ def test_mott_DS_trajectories_vs_reference_golden():
 
 
 def test_mott_statistics_and_refusals():
-    """A Mott run against the float64 Python oracle on other electrons (backscatter coefficient within 3 sigma);
+    """A Mott run against the float64 C oracle on other electrons (backscatter coefficient within 3 sigma, mean
+    trajectory length) and on the same electrons (outcomes);
     continuous mode and a missing table are refused like the reference fails on them."""
     from mcdiscrete_b200.engine import Engine
     from mcdiscrete_b200._lib import MCDError
@@ -859,19 +860,23 @@ def test_mott_statistics_and_refusals():
     n_gpu = 200000
     res = eng.run(count=n_gpu, first_id=0)
     assert res.counters['electrons_done'] == n_gpu
+    import mcd_oracle_cbind as oc
     ip = base_input(elastic='Mott')
     tabs = oracle_tables(golden_tables('Si_15k_small'))
     tabs['Mott'] = o.MottTable(14, 'Si', MOTT_PATH).read_ioffe().to_prob_table()
-    n_ref = 1500
-    els = o.run_electrons(ip, 10 ** 7, n_ref, 12345, tabs)
-    eta_r = np.mean([e.els[0][0] == 'bks' for e in els])
+    n_ref = 60000
+    ref = oc.run(ip, 10 ** 7, n_ref, 12345, tabs, nthreads=os.cpu_count() or 1)      # float64 C oracle, other ids
+    eta_r = float((ref['outcome'] == 1).mean())
     eta_g = float((res.outcome == 1).mean())
-    sd = math.sqrt(eta_r * (1 - eta_r) * (1. / n_gpu + 1. / n_ref))
+    sd = math.sqrt(eta_r * (1 - eta_r) / n_ref + eta_g * (1 - eta_g) / n_gpu)
     print('Mott eta gpu %.4f oracle %.4f (sd %.4f)' % (eta_g, eta_r, sd))
-    assert abs(eta_g - eta_r) < 3.5 * sd, (eta_g, eta_r, sd)
+    assert abs(eta_g - eta_r) < 3 * sd, (eta_g, eta_r, sd)
     # mean number of events per electron against the oracle's (4 standard errors)
-    ne = np.array([len(e.scats) for e in els], float)
+    ne = ref['n_ev'].astype(float)
     assert abs(res.counters['events'] / n_gpu - ne.mean()) < 4 * ne.std() / math.sqrt(n_ref)
+    # same ids, same Philox streams: the float64 oracle's outcome for (nearly) every electron
+    same = oc.run(ip, 0, 20000, ip['seed'], tabs, nthreads=os.cpu_count() or 1)
+    assert (res.outcome[:20000] == same['outcome']).mean() > 0.999
     eng.close()
     with pytest.raises(NotImplementedError):
         Engine(base_input(elastic='Mott', mode='cont'), device=0)

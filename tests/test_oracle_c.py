@@ -170,16 +170,28 @@ def test_c_port_draws_from_the_reference_distributions(tag, kw, tkey):
     reference_sample_checks(c, ref, n)
 
 
-def test_python_port_mott_draws_from_the_reference_distribution():
-    """elastic = 'Mott' (synthetic ioffe-layout table): the Python port against the reference's own-RNG sample (the C
-    port has no Mott channel; the GPU test compares the CUDA path with the same sample)."""
-    ref = dict(np.load(os.path.join(GOLD, 'stats_DS_Si_mott.npz')))
-    ip = dict(E0=20000., Emin=15000., material='Si', s_tilt=70., thickness=3e6, mode='DS', maxScatt=1000, Wc=10., elastic='Mott')
+def _mott_tabs():
     tabs = _golden_tabs('Si_15k_small')
     tabs['Mott'] = o.MottTable(14, 'Si', os.path.join(os.path.dirname(__file__), 'data', 'tables', 'mott') + os.sep).read_ioffe().to_prob_table()
-    n = 1500
-    els = o.run_electrons(ip, 0, n, 777, tabs)
-    sample = dict(outcome=np.array([o.OUTCOMES.index(e.els[0][0]) for e in els]), final_E=np.array([e.els[0][1] for e in els]),
-                  final_dir=np.array([e.els[0][2] for e in els]), last_pos=np.array([e.els[0][3] for e in els]),
-                  n_ev=np.array([len(e.scats) for e in els]))
-    reference_sample_checks(sample, ref, n)
+    return tabs
+
+
+def test_c_port_mott_matches_python_port_and_the_reference_distribution():
+    """elastic = 'Mott' (synthetic ioffe-layout table): the C port follows the Python port event for event (which
+    follows the reference's own golden trajectories, test_oracle_golden.py) and draws from the distributions of the
+    reference's own-RNG sample."""
+    ip = dict(E0=20000., Emin=15000., material='Si', s_tilt=70., thickness=3e6, mode='DS', maxScatt=1000, Wc=10., elastic='Mott')
+    tabs = _mott_tabs()
+    py = o.run_electrons(ip, 50, 24, 999, tabs)
+    ev = [r for e in py for r in e.scats]
+    c = oc.run(ip, 50, 24, 999, tabs, event_rows=len(ev))
+    assert list(c['n_ev']) == [len(e.scats) for e in py]
+    assert list(c['outcome']) == [o.OUTCOMES.index(e.els[0][0]) for e in py]
+    assert list(c['events'][:, 0].astype(int)) == [r['channel'] for r in ev]
+    np.testing.assert_allclose(c['events'][:, 6], [r['pol_angle'] for r in ev], rtol=1e-14)
+    np.testing.assert_allclose(c['final_E'], [e.els[0][1] for e in py], rtol=1e-12)
+    ref = dict(np.load(os.path.join(GOLD, 'stats_DS_Si_mott.npz')))
+    n = 60000
+    reference_sample_checks(oc.run(ip, 0, n, 31337, tabs, nthreads=os.cpu_count() or 1), ref, n)
+    with pytest.raises(ValueError):
+        oc.run(dict(ip, mode='cont'), 0, 4, 1, tabs)
